@@ -1,0 +1,149 @@
+/*
+ * mcevidence_b200 -- C ABI of the B200 kNN-evidence hot path.
+ *
+ * The reference (yabebalFantaye/MCEvidence) has no FFI: its numeric core is the
+ * body of MCEvidence.evidence() (MCEvidence.py:1033-1131) plus scikit-learn's
+ * NearestNeighbors.  This header declares the entry points a maintainer binds
+ * with ctypes in place of those lines:
+ *
+ *   mce_evidence   replaces  get_covariance + diagonalise_chain + NearestNeighbors.fit /
+ *                            kneighbors + the volume/dotp/MLE loop
+ *                            (MCEvidence.py:851-882, 842-849, 1093-1104, 1107-1131)
+ *   mce_knn        replaces  NearestNeighbors(...).fit(ref).kneighbors(query)
+ *                            (MCEvidence.py:1093-1104) with the same (DkNN, indices) contract
+ *   mce_evidence_batch       the per-(model, data, chain) loop of planck_mcevidence.py:306-359
+ *
+ * Plain C types only; every pointer is caller-owned and only has to stay valid
+ * for the duration of the call.  Functions return MCE_OK (0) or a negative code
+ * and never throw or exit; mce_last_error() gives the message (thread-local).
+ * One call at a time per context (internal mutex); contexts are independent.
+ * There is no CPU fallback: without a usable sm_100 device every compute entry
+ * point fails with MCE_ERR_CUDA.
+ */
+#ifndef MCEVIDENCE_B200_H
+#define MCEVIDENCE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCE_ABI_VERSION 1
+
+#define MCE_OK              0
+#define MCE_ERR_ARG        -1   /* bad argument (message says which) */
+#define MCE_ERR_CUDA       -2   /* CUDA runtime / driver error, or no device */
+#define MCE_ERR_NOT_POSDEF -3   /* sample covariance is not positive definite (MCEvidence.py:867) */
+#define MCE_ERR_NOMEM      -4   /* device or host allocation failed */
+#define MCE_ERR_INTERNAL   -5   /* exactness verification failed after the exact re-scan */
+
+#define MCE_MAX_DIM        64   /* largest ndim served by the tiled FP32 filter */
+#define MCE_MAX_NEIGHBOURS 16   /* largest number of true neighbours per sample */
+
+/* mce_problem.flags */
+#define MCE_FLAG_DEVICE_PTRS  1  /* query/ref/logl/weights and result arrays are device pointers on the context's device */
+#define MCE_FLAG_PARTIALS     2  /* also return the per-k (max, sum, sum2) partials (result.partials) */
+#define MCE_FLAG_EXACT_ONLY   4  /* skip the FP32 filter: exhaustive FP64 search for every row (validation) */
+
+typedef struct mce_ctx mce_ctx;
+
+/* One evidence problem = one batch of MCEvidence.evidence() (MCEvidence.py:1041-1131). */
+typedef struct mce_problem {
+    const double *query;     /* s1 samples, (n_query, ld_query) row-major, first d columns used (MCEvidence.py:902) */
+    const double *ref;       /* s2 samples for cross mode (MCEvidence.py:1075-1094), or NULL: auto mode,
+                                neighbours searched in the query set itself with each row excluded (k0=1, :1099) */
+    const double *logl;      /* n_query log-likelihoods: -loglikes, negated again for pos_lnp (MCEvidence.py:399,1060) */
+    const double *weights;   /* n_query sample weights (MCEvidence.py:400,1117) */
+    int64_t n_query;
+    int64_t n_ref;           /* ignored when ref == NULL */
+    int64_t ld_query;        /* row stride of query in doubles (>= d) */
+    int64_t ld_ref;
+    int64_t q_begin;         /* only rows [q_begin, q_end) of query are searched and reduced (row sharding over */
+    int64_t q_end;           /* GPUs); covariance and, in auto mode, the reference set still use all rows. 0,0 = all */
+    int32_t d;               /* ndim */
+    int32_t kmax;            /* reference kmax (clamped to >= 2, MCEvidence.py:694): logE for k = 1..kmax-1 */
+    int32_t flags;
+    int32_t reserved;
+    /* Whitening y = (x - mu) W.  W == NULL: the library estimates the unweighted, ddof=1 covariance of
+       query U ref (np.cov, MCEvidence.py:865), factors it (Cholesky) and sets log J = 0.5 log det C (:877).
+       Otherwise W is d x d row-major (for the reference's own factor: eVec / sqrt(eVal), :844-847),
+       W_ref optionally a different matrix for the ref set (covtype='single', :1080-1086), mu may be NULL (0). */
+    const double *W;
+    const double *W_ref;
+    const double *mu;
+    double log_jacobian;     /* log J, read only when W != NULL */
+    double log_sum_w;        /* log sum of adjusted_weights of s1 (MCEvidence.py:1126) */
+    double log_prior_volume; /* MCEvidence.py:1017-1020 */
+} mce_problem;
+
+typedef struct mce_stats {
+    double ms_total;         /* device time of the whole call (CUDA events on the context stream) */
+    double ms_h2d;           /* host->device copies (0 with MCE_FLAG_DEVICE_PTRS) */
+    double ms_cov;           /* K0 covariance + Cholesky */
+    double ms_whiten;        /* K1 whitening + FP32 tile emission */
+    double ms_filter;        /* K2 tiled FP32 filter (the dominant kernel) */
+    double ms_rerank;        /* K3 FP64 re-rank + verification */
+    double ms_exact;         /* exact FP64 re-scan of unverified rows */
+    double ms_reduce;        /* K4 log-volume + logsumexp epilogue */
+    double ms_d2h;
+    int64_t pairs;           /* pair distances evaluated by the filter = (q_end-q_begin) * n_ref */
+    int64_t rows_rescanned;  /* rows that failed the FP32->FP64 verification and were re-scanned exactly */
+    int32_t launches;        /* kernels launched by this call */
+    int32_t filter_tq;       /* filter configuration actually used */
+    int32_t filter_tr;
+    int32_t filter_packed;
+    int32_t ref_chunks;
+    int32_t list_len;
+    int32_t filter_grid;
+    int32_t filter_smem;
+    int32_t filter_ctas_per_sm;
+    float   rmax;            /* largest whitened reference norm (enters the error bound) */
+    int32_t pad;
+} mce_stats;
+
+typedef struct mce_result {
+    double  *logE;           /* kmax-1 values: MLE[0,1:] of MCEvidence.py:1155-1157 (may be NULL with MCE_FLAG_PARTIALS) */
+    double  *var_logE;       /* kmax-1 delta-method variances of logE, or NULL (no reference counterpart) */
+    double  *dknn;           /* optional (q_end-q_begin, kmax+1) distances shaped like kneighbors() at MCEvidence.py:1104 */
+    int64_t *idx;            /* optional neighbour indices, same shape */
+    double  *partials;       /* with MCE_FLAG_PARTIALS: 3*(kmax-1) doubles (max_t, sum exp(t-max), sum exp(2(t-max))) */
+    double   log_jacobian;   /* log J actually used */
+    mce_stats stats;
+} mce_result;
+
+int         mce_version(void);
+const char *mce_last_error(void);
+int         mce_device_count(void);
+
+int  mce_ctx_create(int device, mce_ctx **out);
+void mce_ctx_destroy(mce_ctx *ctx);
+/* Run on an existing CUDA stream (e.g. torch's current stream) instead of the context's own. NULL restores it. */
+int  mce_ctx_set_stream(mce_ctx *ctx, void *cuda_stream);
+/* Tuning knobs: "filter_tq", "filter_tr", "filter_packed", "ref_chunks", "list_margin", "filter_ctas". -1 = automatic. */
+int  mce_ctx_set_option(mce_ctx *ctx, const char *name, int value);
+
+int  mce_evidence(mce_ctx *ctx, const mce_problem *problem, mce_result *result);
+int  mce_evidence_batch(mce_ctx *ctx, int n, const mce_problem *problems, mce_result *results);
+
+/* k nearest neighbours with sklearn's contract: dknn/idx are (q_end-q_begin, n_neighbors), ascending.
+   Auto mode (ref == NULL): column 0 is the row itself at distance 0, as when the reference queries the
+   fitted set with itself (MCEvidence.py:1101-1104).  Only the sample arrays, their sizes and strides, the row range, d, the whitening fields and
+   flags are read. */
+int  mce_knn(mce_ctx *ctx, const mce_problem *problem, int n_neighbors, double *dknn, int64_t *idx, mce_stats *stats);
+
+/* Host arithmetic shared by the single- and multi-GPU paths.
+   Combine `nparts` partial triples (each 3*nk doubles) into one. */
+int  mce_combine_partials(int nparts, int nk, const double *parts, double *out);
+/* logE_k = log SumW + log J - log PV - log(S k_nn + 1) + log c_d + max_k + log sum_k  (MCEvidence.py:1117-1131) */
+int  mce_finalize(const double *partials, int nk, int d, int cross, int64_t n_query_total, double log_sum_w,
+                  double log_jacobian, double log_prior_volume, double *logE, double *var_logE);
+
+/* FP32 FMA microbenchmark on the context's device: variant 0 = scalar FFMA, 1 = packed FFMA2.
+   Reports achieved TFLOP/s counting 2 FLOP per lane-FMA, the roofline denominator of the filter. */
+int  mce_fma_peak(mce_ctx *ctx, int variant, int iters, double *tflops, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCEVIDENCE_B200_H */

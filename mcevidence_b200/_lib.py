@@ -1,0 +1,276 @@
+"""ctypes binding of ``libmcevidence_b200.so`` (C ABI in ``include/mcevidence_b200.h``).
+
+This is the whole Python<->CUDA boundary of the package: plain pointers and
+sizes, no torch types.  There is no CPU fallback -- if the shared library is
+missing or no sm_100 device is usable, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+MCE_MAX_DIM = 64
+MCE_MAX_NEIGHBOURS = 16
+FLAG_DEVICE_PTRS = 1
+FLAG_PARTIALS = 2
+FLAG_EXACT_ONLY = 4
+
+ERR_NOT_POSDEF = -3
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libmcevidence_b200.so')
+
+c_double_p = C.POINTER(C.c_double)
+c_int64_p = C.POINTER(C.c_int64)
+
+
+class Problem(C.Structure):
+    _fields_ = [
+        ('query', C.c_void_p), ('ref', C.c_void_p), ('logl', C.c_void_p), ('weights', C.c_void_p),
+        ('n_query', C.c_int64), ('n_ref', C.c_int64), ('ld_query', C.c_int64), ('ld_ref', C.c_int64),
+        ('q_begin', C.c_int64), ('q_end', C.c_int64),
+        ('d', C.c_int32), ('kmax', C.c_int32), ('flags', C.c_int32), ('reserved', C.c_int32),
+        ('W', C.c_void_p), ('W_ref', C.c_void_p), ('mu', C.c_void_p),
+        ('log_jacobian', C.c_double), ('log_sum_w', C.c_double), ('log_prior_volume', C.c_double),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ('ms_total', C.c_double), ('ms_h2d', C.c_double), ('ms_cov', C.c_double), ('ms_whiten', C.c_double),
+        ('ms_filter', C.c_double), ('ms_rerank', C.c_double), ('ms_exact', C.c_double), ('ms_reduce', C.c_double),
+        ('ms_d2h', C.c_double),
+        ('pairs', C.c_int64), ('rows_rescanned', C.c_int64),
+        ('launches', C.c_int32), ('filter_tq', C.c_int32), ('filter_tr', C.c_int32), ('filter_packed', C.c_int32),
+        ('ref_chunks', C.c_int32), ('list_len', C.c_int32), ('filter_grid', C.c_int32), ('filter_smem', C.c_int32),
+        ('filter_ctas_per_sm', C.c_int32), ('rmax', C.c_float), ('pad', C.c_int32),
+    ]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_ if name != 'pad'}
+
+
+class Result(C.Structure):
+    _fields_ = [
+        ('logE', C.c_void_p), ('var_logE', C.c_void_p), ('dknn', C.c_void_p), ('idx', C.c_void_p),
+        ('partials', C.c_void_p), ('log_jacobian', C.c_double), ('stats', Stats),
+    ]
+
+
+class MCEError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__('mcevidence_b200 error %d: %s' % (code, message))
+        self.code = code
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    """Load the CUDA shared library; raise if it has not been built (no fallback)."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                'mcevidence_b200: %s not found. Build it with `make -C mcevidence_b200/csrc -j8` '
+                '(or `python -c "import __graft_entry__ as g; g.build()"`). There is no CPU fallback.' % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        lib.mce_version.restype = C.c_int
+        lib.mce_last_error.restype = C.c_char_p
+        lib.mce_device_count.restype = C.c_int
+        lib.mce_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        lib.mce_ctx_destroy.argtypes = [C.c_void_p]
+        lib.mce_ctx_destroy.restype = None
+        lib.mce_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        lib.mce_ctx_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        lib.mce_evidence.argtypes = [C.c_void_p, C.POINTER(Problem), C.POINTER(Result)]
+        lib.mce_evidence_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(Problem), C.POINTER(Result)]
+        lib.mce_knn.argtypes = [C.c_void_p, C.POINTER(Problem), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Stats)]
+        lib.mce_combine_partials.argtypes = [C.c_int, C.c_int, c_double_p, c_double_p]
+        lib.mce_finalize.argtypes = [c_double_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_double,
+                                     C.c_double, c_double_p, c_double_p]
+        lib.mce_fma_peak.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p]
+        _lib = lib
+        return lib
+
+
+def _check(lib, rc):
+    if rc != 0:
+        raise MCEError(rc, lib.mce_last_error().decode('utf-8', 'replace'))
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def _f64(a, name):
+    """float64 array whose rows are contiguous (strided rows are passed through ``ld``)."""
+    a = np.asarray(a)
+    if a.dtype != np.float64:
+        a = a.astype(np.float64)
+    if a.ndim == 2:
+        if a.strides[1] != 8 or a.strides[0] % 8 or a.strides[0] < 8 * a.shape[1]:
+            a = np.ascontiguousarray(a)
+    elif not a.flags.c_contiguous:
+        a = np.ascontiguousarray(a)
+    return a
+
+
+class Context:
+    """One CUDA stream + workspace on one device (``mce_ctx``)."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        h = C.c_void_p()
+        _check(self._lib, self._lib.mce_ctx_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._lib.mce_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        _check(self._lib, self._lib.mce_ctx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def set_option(self, name, value):
+        _check(self._lib, self._lib.mce_ctx_set_option(self._h, name.encode(), int(value)))
+
+    # ------------------------------------------------------------------
+    def _problem(self, query, ref, logl, weights, ndim, kmax, W, W_ref, mu, log_jacobian, log_sum_w,
+                 log_prior_volume, q_range, flags, keep):
+        p = Problem()
+        query = _f64(query, 'query')
+        keep.append(query)
+        if query.ndim != 2:
+            raise ValueError('query must be 2-D')
+        ndim = int(query.shape[1] if ndim is None else ndim)
+        if ndim > query.shape[1]:
+            raise ValueError('ndim=%d exceeds the %d sample columns' % (ndim, query.shape[1]))
+        p.query = _ptr(query)
+        p.n_query, p.ld_query = query.shape[0], query.strides[0] // 8
+        if ref is not None:
+            ref = _f64(ref, 'ref')
+            keep.append(ref)
+            if ref.ndim != 2 or ref.shape[1] < ndim:
+                raise ValueError('ref must be 2-D with at least ndim columns')
+            p.ref = _ptr(ref)
+            p.n_ref, p.ld_ref = ref.shape[0], ref.strides[0] // 8
+        for name, arr in (('logl', logl), ('weights', weights)):
+            if arr is not None:
+                arr = _f64(arr, name).reshape(-1)
+                if arr.shape[0] != query.shape[0]:
+                    raise ValueError('%s has %d entries for %d samples' % (name, arr.shape[0], query.shape[0]))
+                keep.append(arr)
+                setattr(p, name, _ptr(arr))
+        for name, arr, shape in (('W', W, (ndim, ndim)), ('W_ref', W_ref, (ndim, ndim)), ('mu', mu, (ndim,))):
+            if arr is not None:
+                arr = np.ascontiguousarray(arr, dtype=np.float64)
+                if arr.shape != shape:
+                    raise ValueError('%s must have shape %s' % (name, shape))
+                keep.append(arr)
+                setattr(p, name, _ptr(arr))
+        if q_range is not None:
+            p.q_begin, p.q_end = int(q_range[0]), int(q_range[1])
+        p.d, p.kmax, p.flags = ndim, int(kmax), int(flags)
+        p.log_jacobian, p.log_sum_w, p.log_prior_volume = float(log_jacobian), float(log_sum_w), float(log_prior_volume)
+        nq = (p.q_end - p.q_begin) if p.q_end else p.n_query
+        return p, nq
+
+    def evidence(self, query, logl, weights, kmax, ref=None, ndim=None, W=None, W_ref=None, mu=None,
+                 log_jacobian=0.0, log_sum_w=0.0, log_prior_volume=0.0, q_range=None, want_knn=False,
+                 want_partials=False, exact_only=False):
+        """``mce_evidence`` on host arrays.  Returns a dict with ``logE`` (kmax-1), ``var_logE``,
+        ``log_jacobian``, ``stats`` and optionally ``dknn``/``idx``/``partials``."""
+        keep = []
+        flags = (FLAG_PARTIALS if want_partials else 0) | (FLAG_EXACT_ONLY if exact_only else 0)
+        p, nq = self._problem(query, ref, logl, weights, ndim, kmax, W, W_ref, mu, log_jacobian, log_sum_w,
+                              log_prior_volume, q_range, flags, keep)
+        kk = max(2, int(kmax))
+        r = Result()
+        loge = np.empty(kk - 1)
+        var = np.empty(kk - 1)
+        r.logE, r.var_logE = _ptr(loge), _ptr(var)
+        out = {}
+        if want_knn:
+            out['dknn'] = np.empty((nq, kk + 1))
+            out['idx'] = np.empty((nq, kk + 1), dtype=np.int64)
+            r.dknn, r.idx = _ptr(out['dknn']), _ptr(out['idx'])
+        if want_partials:
+            out['partials'] = np.empty((kk - 1, 3))
+            r.partials = _ptr(out['partials'])
+        _check(self._lib, self._lib.mce_evidence(self._h, C.byref(p), C.byref(r)))
+        out.update({'logE': loge, 'var_logE': var, 'log_jacobian': r.log_jacobian, 'stats': r.stats.as_dict()})
+        return out
+
+    def knn(self, query, n_neighbors, ref=None, ndim=None, W=None, W_ref=None, mu=None, q_range=None,
+            exact_only=False, identity=False):
+        """``mce_knn``: ``(dknn, idx, stats)`` with sklearn's ``kneighbors`` contract.
+        ``identity=True`` searches the coordinates as given (W = I, mu = 0)."""
+        keep = []
+        query_a = np.asarray(query)
+        nd = int(query_a.shape[1] if ndim is None else ndim)
+        if identity:
+            W = np.eye(nd)
+        p, nq = self._problem(query, ref, None, None, nd, 2, W, W_ref, mu, 0.0, 0.0, 0.0, q_range,
+                              FLAG_EXACT_ONLY if exact_only else 0, keep)
+        dknn = np.empty((nq, int(n_neighbors)))
+        idx = np.empty((nq, int(n_neighbors)), dtype=np.int64)
+        st = Stats()
+        _check(self._lib, self._lib.mce_knn(self._h, C.byref(p), int(n_neighbors), _ptr(dknn), _ptr(idx), C.byref(st)))
+        return dknn, idx, st.as_dict()
+
+    def evidence_device(self, problem, result):
+        """Raw call with a caller-filled ``Problem`` (device pointers) and ``Result``."""
+        _check(self._lib, self._lib.mce_evidence(self._h, C.byref(problem), C.byref(result)))
+
+    def fma_peak(self, variant=1, iters=4096):
+        tf, ms = C.c_double(), C.c_double()
+        _check(self._lib, self._lib.mce_fma_peak(self._h, int(variant), int(iters), C.byref(tf), C.byref(ms)))
+        return tf.value, ms.value
+
+
+def combine_partials(parts):
+    """``mce_combine_partials`` on an array of shape (nparts, nk, 3)."""
+    lib = load_library()
+    parts = np.ascontiguousarray(parts, dtype=np.float64)
+    nparts, nk, _ = parts.shape
+    out = np.empty((nk, 3))
+    _check(lib, lib.mce_combine_partials(nparts, nk, parts.ctypes.data_as(c_double_p), out.ctypes.data_as(c_double_p)))
+    return out
+
+
+def finalize(partials, ndim, cross, n_query_total, log_sum_w, log_jacobian, log_prior_volume):
+    """``mce_finalize``: partial triples -> (logE, var_logE)."""
+    lib = load_library()
+    partials = np.ascontiguousarray(partials, dtype=np.float64)
+    nk = partials.shape[0]
+    loge, var = np.empty(nk), np.empty(nk)
+    _check(lib, lib.mce_finalize(partials.ctypes.data_as(c_double_p), nk, int(ndim), int(bool(cross)),
+                                 int(n_query_total), float(log_sum_w), float(log_jacobian),
+                                 float(log_prior_volume), loge.ctypes.data_as(c_double_p),
+                                 var.ctypes.data_as(c_double_p)))
+    return loge, var
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    ctx = _default_ctx.get(device)
+    if ctx is None:
+        ctx = _default_ctx[device] = Context(device)
+    return ctx

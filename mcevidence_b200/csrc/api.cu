@@ -1,0 +1,666 @@
+// C ABI of libmcevidence_b200.so (declared in include/mcevidence_b200.h): context, workspace,
+// host<->device staging and the stream-ordered pipeline K0 -> K1 -> K2 -> K3 -> (exact) -> K4.
+// No CPU fallback: every compute entry point needs an sm_100 device.
+#include "../../include/mcevidence_b200.h"
+#include "common.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <new>
+
+using namespace mce;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            const int code_ = (e_ == cudaErrorMemoryAllocation) ? MCE_ERR_NOMEM : MCE_ERR_CUDA;        \
+            return fail(code_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                              \
+    } while (0)
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return MCE_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + (bytes >> 3) + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            e = cudaMalloc(&p, bytes);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return fail(MCE_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+            }
+            cap = bytes;
+            return MCE_OK;
+        }
+        cap = want;
+        return MCE_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct DevScalars {
+    double out[3 * (MCE_MAX_NEIGHBOURS + 1)];
+    double logj;
+    double mean[MCE_MAX_DIM];
+    double W[MCE_MAX_DIM * MCE_MAX_DIM];
+    double W_ref[MCE_MAX_DIM * MCE_MAX_DIM];
+    int status;
+    int nflagged;
+    unsigned int rmax_bits;
+    int pad;
+};
+
+enum { EV_START, EV_H2D, EV_COV, EV_WHITEN, EV_FILTER, EV_RERANK, EV_EXACT, EV_REDUCE, EV_END, EV_COUNT };
+
+}  // namespace
+
+struct mce_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    int opt_tq = -1, opt_tr = -1, opt_packed = -1, opt_chunks = -1, opt_margin = -1, opt_ctas = -1;
+    DevBuf xq, xr, logl, w, yr, yq, tiles, cand_idx, cand_th, dknn, idx, flagged, covpart, redpart, scal, sink;
+    DevScalars* hscal = nullptr;  // pinned
+    cudaEvent_t ev[EV_COUNT] = {};
+};
+
+namespace {
+
+int validate(const mce_problem* p, bool need_evidence) {
+    if (!p) return fail(MCE_ERR_ARG, "problem is NULL");
+    if (!p->query) return fail(MCE_ERR_ARG, "problem.query is NULL");
+    if (p->d < 1 || p->d > MCE_MAX_DIM) return fail(MCE_ERR_ARG, "ndim=%d outside [1, %d]", p->d, MCE_MAX_DIM);
+    if (p->n_query < 1) return fail(MCE_ERR_ARG, "n_query=%lld must be positive", (long long)p->n_query);
+    if (p->ld_query < p->d) return fail(MCE_ERR_ARG, "ld_query=%lld < ndim=%d", (long long)p->ld_query, p->d);
+    if (p->ref) {
+        if (p->n_ref < 1) return fail(MCE_ERR_ARG, "n_ref=%lld must be positive", (long long)p->n_ref);
+        if (p->ld_ref < p->d) return fail(MCE_ERR_ARG, "ld_ref=%lld < ndim=%d", (long long)p->ld_ref, p->d);
+    }
+    const long long nref = p->ref ? p->n_ref : p->n_query;
+    if (nref >= 0x7fffffffLL) return fail(MCE_ERR_ARG, "reference set of %lld rows exceeds 2^31-1", nref);
+    if (p->q_begin < 0 || p->q_end < 0 || p->q_end > p->n_query || (p->q_end != 0 && p->q_begin >= p->q_end))
+        return fail(MCE_ERR_ARG, "bad query row range [%lld, %lld) for n_query=%lld", (long long)p->q_begin,
+                    (long long)p->q_end, (long long)p->n_query);
+    if (need_evidence) {
+        if (!p->logl || !p->weights) return fail(MCE_ERR_ARG, "problem.logl / problem.weights is NULL");
+    }
+    if (p->W_ref && !p->W) return fail(MCE_ERR_ARG, "W_ref given without W");
+    return MCE_OK;
+}
+
+struct Run {
+    // inputs
+    const mce_problem* p;
+    bool evidence;
+    int n_neighbors;  // knn mode only
+    double* dknn_out;
+    int64_t* idx_out;
+    mce_result* res;
+    mce_stats* stats;
+};
+
+int run_problem(mce_ctx* c, const Run& r) {
+    const mce_problem& p = *r.p;
+    int rc = validate(&p, r.evidence);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const bool devptr = (p.flags & MCE_FLAG_DEVICE_PTRS) != 0;
+    const bool cross = p.ref != nullptr;
+    const int d = p.d;
+    const long long nq_all = p.n_query;
+    const long long n_ref = cross ? p.n_ref : nq_all;
+    const long long qb = p.q_begin, qe = (p.q_end == 0) ? nq_all : p.q_end;
+    const long long nq = qe - qb;
+    const int kmax = p.kmax < 2 ? 2 : p.kmax;
+
+    // number of true neighbours and output shape
+    int K, out_cols, out_col0, write_self;
+    double* user_dknn;
+    int64_t* user_idx;
+    if (r.evidence) {
+        user_dknn = r.res->dknn;
+        user_idx = r.res->idx;
+        const bool shaped = user_dknn || user_idx;
+        if (shaped) {  // kneighbors-shaped (nq, kmax+1) output requested (MCEvidence.py:1104)
+            out_cols = kmax + 1;
+            out_col0 = cross ? 0 : 1;
+            write_self = cross ? 0 : 1;
+            K = cross ? kmax + 1 : kmax;
+        } else {       // only what the estimator reads: neighbours 1..kmax-1 (auto) / 2..kmax (cross), F7
+            K = cross ? kmax : kmax - 1;
+            out_cols = K;
+            out_col0 = 0;
+            write_self = 0;
+        }
+    } else {
+        user_dknn = r.dknn_out;
+        user_idx = r.idx_out;
+        out_cols = r.n_neighbors;
+        out_col0 = cross ? 0 : 1;
+        write_self = cross ? 0 : 1;
+        K = cross ? r.n_neighbors : r.n_neighbors - 1;
+        if (!user_dknn) return fail(MCE_ERR_ARG, "dknn output is NULL");
+    }
+    if (K < 1 || K > MCE_MAX_NEIGHBOURS)
+        return fail(MCE_ERR_ARG, "number of neighbours %d outside [1, %d]", K, MCE_MAX_NEIGHBOURS);
+    if (n_ref - (cross ? 0 : 1) < K)
+        return fail(MCE_ERR_ARG, "Expected n_neighbors <= n_samples_fit: %d neighbours from %lld reference rows", K,
+                    n_ref - (cross ? 0 : 1));
+
+    int launches = 0;
+    CU(cudaEventRecord(c->ev[EV_START], st));
+
+    // ---- inputs on the device ------------------------------------------------------------
+    const double *dq, *dr = nullptr, *dlogl = nullptr, *dw = nullptr;
+    long long ldq = p.ld_query, ldr = p.ld_ref;
+    if (devptr) {
+        dq = p.query;
+        dr = p.ref;
+        dlogl = p.logl;
+        dw = p.weights;
+    } else {
+        rc = c->xq.ensure((size_t)nq_all * d * sizeof(double));
+        if (rc) return rc;
+        if (p.ld_query == d)
+            CU(cudaMemcpyAsync(c->xq.p, p.query, (size_t)nq_all * d * 8, cudaMemcpyHostToDevice, st));
+        else
+            CU(cudaMemcpy2DAsync(c->xq.p, (size_t)d * 8, p.query, (size_t)p.ld_query * 8, (size_t)d * 8,
+                                 (size_t)nq_all, cudaMemcpyHostToDevice, st));
+        dq = c->xq.as<double>();
+        ldq = d;
+        if (cross) {
+            rc = c->xr.ensure((size_t)n_ref * d * sizeof(double));
+            if (rc) return rc;
+            if (p.ld_ref == d)
+                CU(cudaMemcpyAsync(c->xr.p, p.ref, (size_t)n_ref * d * 8, cudaMemcpyHostToDevice, st));
+            else
+                CU(cudaMemcpy2DAsync(c->xr.p, (size_t)d * 8, p.ref, (size_t)p.ld_ref * 8, (size_t)d * 8,
+                                     (size_t)n_ref, cudaMemcpyHostToDevice, st));
+            dr = c->xr.as<double>();
+            ldr = d;
+        }
+        if (r.evidence) {
+            rc = c->logl.ensure((size_t)nq * 8);
+            if (rc) return rc;
+            rc = c->w.ensure((size_t)nq * 8);
+            if (rc) return rc;
+            CU(cudaMemcpyAsync(c->logl.p, p.logl + qb, (size_t)nq * 8, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(c->w.p, p.weights + qb, (size_t)nq * 8, cudaMemcpyHostToDevice, st));
+            dlogl = c->logl.as<double>() - qb;  // indexed by global row
+            dw = c->w.as<double>() - qb;
+        }
+    }
+    CU(cudaEventRecord(c->ev[EV_H2D], st));
+
+    // ---- K0: whitening matrix -------------------------------------------------------------
+    rc = c->scal.ensure(sizeof(DevScalars));
+    if (rc) return rc;
+    DevScalars* ds = c->scal.as<DevScalars>();
+    CU(cudaMemsetAsync(&ds->status, 0, 4 * sizeof(int), st));  // status, nflagged, rmax_bits, pad
+    const double *dW, *dWr, *dmu;
+    if (!p.W) {
+        const int grid = cov_grid_size(c->sm_count);
+        const int npairs = d * (d + 1) / 2;
+        rc = c->covpart.ensure((size_t)grid * (npairs > d ? npairs : d) * 8);
+        if (rc) return rc;
+        CovWorkspace ws{c->covpart.as<double>(), ds->mean, ds->W, &ds->logj, &ds->status};
+        Segment a{dq, nq_all, ldq};
+        Segment b{cross ? dr : nullptr, cross ? n_ref : 0, ldr};
+        launch_covariance(a, b, d, ws, grid, st, &launches);
+        dW = ds->W;
+        dWr = ds->W;
+        dmu = ds->mean;
+    } else {
+        CU(cudaMemcpyAsync(ds->W, p.W, (size_t)d * d * 8, cudaMemcpyHostToDevice, st));
+        dW = ds->W;
+        dWr = ds->W;
+        if (p.W_ref) {
+            CU(cudaMemcpyAsync(ds->W_ref, p.W_ref, (size_t)d * d * 8, cudaMemcpyHostToDevice, st));
+            dWr = ds->W_ref;
+        }
+        if (p.mu) {
+            CU(cudaMemcpyAsync(ds->mean, p.mu, (size_t)d * 8, cudaMemcpyHostToDevice, st));
+            dmu = ds->mean;
+        } else {
+            dmu = nullptr;
+        }
+        CU(cudaMemcpyAsync(&ds->logj, &p.log_jacobian, 8, cudaMemcpyHostToDevice, st));
+    }
+    CU(cudaEventRecord(c->ev[EV_COV], st));
+
+    // ---- K1: whitening on load ------------------------------------------------------------
+    const int ntiles = (int)((n_ref + TILE_REFS - 1) / TILE_REFS);
+    rc = c->yr.ensure((size_t)n_ref * d * 8);
+    if (rc) return rc;
+    rc = c->tiles.ensure((size_t)ntiles * (d + 1) * TILE_REFS * sizeof(float));
+    if (rc) return rc;
+    const double* yq_base;
+    if (cross) {
+        launch_whiten(Segment{dr, n_ref, ldr}, d, dWr, dmu, c->yr.as<double>(), c->tiles.as<float>(), &ds->rmax_bits, st,
+                      &launches);
+        rc = c->yq.ensure((size_t)nq * d * 8);
+        if (rc) return rc;
+        launch_whiten(Segment{dq + qb * ldq, nq, ldq}, d, dW, dmu, c->yq.as<double>(), nullptr, nullptr, st, &launches);
+        yq_base = c->yq.as<double>() - qb * d;
+    } else {
+        launch_whiten(Segment{dq, nq_all, ldq}, d, dW, dmu, c->yr.as<double>(), c->tiles.as<float>(), &ds->rmax_bits, st,
+                      &launches);
+        yq_base = c->yr.as<double>();
+    }
+    CU(cudaEventRecord(c->ev[EV_WHITEN], st));
+
+    // ---- K2: FP32 filter ---------------------------------------------------------------------
+    const bool exact_only = (p.flags & MCE_FLAG_EXACT_ONLY) != 0;
+    const int margin = c->opt_margin >= 0 ? c->opt_margin : 2;
+    int list_len = K + margin;
+    FilterConfig cfg;
+    filter_default_config(d, list_len, &cfg);
+    if (c->opt_tq > 0) cfg.tq = c->opt_tq;
+    if (c->opt_tr > 0) cfg.tr = c->opt_tr;
+    if (c->opt_packed >= 0) cfg.packed = c->opt_packed;
+    int qpc = 0, smem = 0, ctas = 0;
+    if (filter_query(d, cfg, list_len, &qpc, &smem, &ctas) != 0) {
+        cudaGetLastError();
+        FilterConfig def;
+        filter_default_config(d, list_len, &def);
+        if (filter_query(d, def, list_len, &qpc, &smem, &ctas) != 0) {
+            cudaGetLastError();
+            return fail(MCE_ERR_ARG, "no filter kernel for ndim=%d tq=%d tr=%d packed=%d list_len=%d", d, cfg.tq, cfg.tr,
+                        cfg.packed, list_len);
+        }
+        cfg = def;
+    }
+    const int nqblocks = (int)((nq + qpc - 1) / qpc);
+    const long long nq_pad = (long long)nqblocks * qpc;
+    int chunks;
+    if (c->opt_chunks > 0) {
+        chunks = c->opt_chunks;
+    } else {
+        const long long slots = (long long)c->sm_count * ctas;
+        const long long target = 16 * slots;
+        chunks = (int)((target + nqblocks - 1) / nqblocks);
+        const int max_chunks = ntiles / 4 > 1 ? ntiles / 4 : 1;
+        if (chunks > max_chunks) chunks = max_chunks;
+        if (chunks > 64) chunks = 64;
+        if (chunks < 1) chunks = 1;
+    }
+    if (chunks > ntiles) chunks = ntiles;
+    const int tiles_per_chunk = (ntiles + chunks - 1) / chunks;
+    chunks = (ntiles + tiles_per_chunk - 1) / tiles_per_chunk;
+
+    rc = c->cand_idx.ensure((size_t)chunks * list_len * nq_pad * sizeof(int));
+    if (rc) return rc;
+    rc = c->cand_th.ensure((size_t)chunks * nq_pad * sizeof(float));
+    if (rc) return rc;
+    rc = c->flagged.ensure((size_t)nq * sizeof(int));
+    if (rc) return rc;
+
+    if (!exact_only) {
+        FilterParams fp;
+        fp.yq = yq_base;
+        fp.tiles = c->tiles.as<float>();
+        fp.cand_idx = c->cand_idx.as<int>();
+        fp.cand_th = c->cand_th.as<float>();
+        fp.q_begin = qb;
+        fp.q_end = qe;
+        fp.nq_pad = nq_pad;
+        fp.self_offset = 0;
+        fp.self_exclude = cross ? 0 : 1;
+        fp.ntiles = ntiles;
+        fp.tiles_per_chunk = tiles_per_chunk;
+        fp.ref_chunks = chunks;
+        fp.nqblocks = nqblocks;
+        fp.list_len = list_len;
+        fp.d = d;
+        if (launch_filter(fp, cfg, st, &launches) != 0)
+            return fail(MCE_ERR_CUDA, "filter launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    CU(cudaEventRecord(c->ev[EV_FILTER], st));
+
+    // ---- K3: FP64 re-rank + verification; exact re-scan of unverified rows --------------
+    double* d_dknn;
+    long long* d_idx = nullptr;
+    if (devptr && user_dknn) {
+        d_dknn = user_dknn;
+    } else {
+        rc = c->dknn.ensure((size_t)nq * out_cols * 8);
+        if (rc) return rc;
+        d_dknn = c->dknn.as<double>();
+    }
+    if (user_idx) {
+        if (devptr) {
+            d_idx = reinterpret_cast<long long*>(user_idx);
+        } else {
+            rc = c->idx.ensure((size_t)nq * out_cols * 8);
+            if (rc) return rc;
+            d_idx = c->idx.as<long long>();
+        }
+    }
+    RerankParams rp;
+    rp.yq = yq_base;
+    rp.yr = c->yr.as<double>();
+    rp.cand_idx = c->cand_idx.as<int>();
+    rp.cand_th = c->cand_th.as<float>();
+    rp.rmax_bits = &ds->rmax_bits;
+    rp.dknn = d_dknn;
+    rp.idx = d_idx;
+    rp.flagged = c->flagged.as<int>();
+    rp.nflagged = &ds->nflagged;
+    rp.q_begin = qb;
+    rp.q_end = qe;
+    rp.nq_pad = nq_pad;
+    rp.n_ref = n_ref;
+    rp.self_offset = 0;
+    rp.self_exclude = cross ? 0 : 1;
+    rp.ref_chunks = chunks;
+    rp.list_len = list_len;
+    rp.d = d;
+    rp.k = K;
+    rp.out_ld = out_cols;
+    rp.out_col0 = out_col0;
+    rp.write_self_col = write_self;
+    rp.flag_all = exact_only ? 1 : 0;
+    launch_rerank(rp, st, &launches);
+    CU(cudaEventRecord(c->ev[EV_RERANK], st));
+    launch_exact_rescan(rp, c->sm_count * 4, st, &launches);
+    CU(cudaEventRecord(c->ev[EV_EXACT], st));
+
+    // ---- K4: epilogue -------------------------------------------------------------------------
+    const int nk = kmax - 1;
+    if (r.evidence) {
+        const int rgrid = reduce_grid_size(nq);
+        rc = c->redpart.ensure((size_t)rgrid * nk * 3 * 8);
+        if (rc) return rc;
+        ReduceParams ep;
+        ep.dknn = d_dknn;
+        ep.logl = dlogl;
+        ep.weights = dw;
+        ep.block_partial = c->redpart.as<double>();
+        ep.out = ds->out;
+        ep.q_begin = qb;
+        ep.q_end = qe;
+        ep.ld = out_cols;
+        ep.col0 = out_col0;
+        ep.first_nb = cross ? 2 : 1;
+        ep.nk = nk;
+        ep.d = d;
+        launch_reduce(ep, rgrid, st, &launches);
+    }
+    CU(cudaEventRecord(c->ev[EV_REDUCE], st));
+
+    // ---- results back ---------------------------------------------------------------------------
+    CU(cudaMemcpyAsync(c->hscal, ds, offsetof(DevScalars, mean), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&c->hscal->status, &ds->status, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (!devptr) {
+        if (user_dknn) CU(cudaMemcpyAsync(user_dknn, d_dknn, (size_t)nq * out_cols * 8, cudaMemcpyDeviceToHost, st));
+        if (user_idx) CU(cudaMemcpyAsync(user_idx, d_idx, (size_t)nq * out_cols * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaEventRecord(c->ev[EV_END], st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+
+    if (c->hscal->status != 0)
+        return fail(MCE_ERR_NOT_POSDEF,
+                    "sample covariance of the %d selected parameters is not positive definite "
+                    "(reference: negative eigenvalue warning, MCEvidence.py:867)", d);
+
+    mce_stats sst;
+    memset(&sst, 0, sizeof(sst));
+    float ms = 0.f;
+    auto el = [&](int a, int b) { cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]); return (double)ms; };
+    sst.ms_total = el(EV_START, EV_END);
+    sst.ms_h2d = el(EV_START, EV_H2D);
+    sst.ms_cov = el(EV_H2D, EV_COV);
+    sst.ms_whiten = el(EV_COV, EV_WHITEN);
+    sst.ms_filter = el(EV_WHITEN, EV_FILTER);
+    sst.ms_rerank = el(EV_FILTER, EV_RERANK);
+    sst.ms_exact = el(EV_RERANK, EV_EXACT);
+    sst.ms_reduce = el(EV_EXACT, EV_REDUCE);
+    sst.ms_d2h = el(EV_REDUCE, EV_END);
+    sst.pairs = nq * n_ref;
+    sst.rows_rescanned = c->hscal->nflagged;
+    sst.launches = launches;
+    sst.filter_tq = cfg.tq;
+    sst.filter_tr = cfg.tr;
+    sst.filter_packed = cfg.packed;
+    sst.ref_chunks = chunks;
+    sst.list_len = list_len;
+    sst.filter_grid = nqblocks * chunks;
+    sst.filter_smem = smem;
+    sst.filter_ctas_per_sm = ctas;
+    memcpy(&sst.rmax, &c->hscal->rmax_bits, 4);
+
+    if (r.evidence) {
+        mce_result* res = r.res;
+        res->stats = sst;
+        res->log_jacobian = c->hscal->logj;
+        if ((p.flags & MCE_FLAG_PARTIALS) && res->partials) memcpy(res->partials, c->hscal->out, (size_t)nk * 3 * 8);
+        if (res->logE) {
+            rc = mce_finalize(c->hscal->out, nk, d, cross ? 1 : 0, nq_all, p.log_sum_w, c->hscal->logj,
+                              p.log_prior_volume, res->logE, res->var_logE);
+            if (rc) return rc;
+        }
+    } else if (r.stats) {
+        *r.stats = sst;
+    }
+    return MCE_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int mce_version(void) { return MCE_ABI_VERSION; }
+
+const char* mce_last_error(void) { return g_err; }
+
+int mce_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int mce_ctx_create(int device, mce_ctx** out) {
+    if (!out) return fail(MCE_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(MCE_ERR_CUDA, "no CUDA device available (%s); mcevidence_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= n) return fail(MCE_ERR_ARG, "device %d outside [0, %d)", device, n);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(MCE_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
+                    prop.minor);
+    mce_ctx* c = new (std::nothrow) mce_ctx();
+    if (!c) return fail(MCE_ERR_NOMEM, "out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost(reinterpret_cast<void**>(&c->hscal), sizeof(DevScalars)) != cudaSuccess) {
+        const char* msg = cudaGetErrorString(cudaGetLastError());
+        delete c;
+        return fail(MCE_ERR_CUDA, "context setup failed: %s", msg);
+    }
+    c->stream = c->own_stream;
+    for (int i = 0; i < EV_COUNT; ++i) {
+        if (cudaEventCreate(&c->ev[i]) != cudaSuccess) {
+            mce_ctx_destroy(c);
+            return fail(MCE_ERR_CUDA, "cudaEventCreate failed");
+        }
+    }
+    *out = c;
+    return MCE_OK;
+}
+
+void mce_ctx_destroy(mce_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    DevBuf* bufs[] = {&c->xq, &c->xr, &c->logl, &c->w, &c->yr, &c->yq, &c->tiles, &c->cand_idx, &c->cand_th,
+                      &c->dknn, &c->idx, &c->flagged, &c->covpart, &c->redpart, &c->scal, &c->sink};
+    for (DevBuf* b : bufs) b->release();
+    for (int i = 0; i < EV_COUNT; ++i)
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->hscal) cudaFreeHost(c->hscal);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int mce_ctx_set_stream(mce_ctx* c, void* cuda_stream) {
+    if (!c) return fail(MCE_ERR_ARG, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return MCE_OK;
+}
+
+int mce_ctx_set_option(mce_ctx* c, const char* name, int value) {
+    if (!c || !name) return fail(MCE_ERR_ARG, "ctx or name is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!strcmp(name, "filter_tq")) c->opt_tq = value;
+    else if (!strcmp(name, "filter_tr")) c->opt_tr = value;
+    else if (!strcmp(name, "filter_packed")) c->opt_packed = value;
+    else if (!strcmp(name, "ref_chunks")) c->opt_chunks = value;
+    else if (!strcmp(name, "list_margin")) c->opt_margin = value;
+    else if (!strcmp(name, "filter_ctas")) c->opt_ctas = value;
+    else return fail(MCE_ERR_ARG, "unknown option '%s'", name);
+    return MCE_OK;
+}
+
+int mce_evidence(mce_ctx* c, const mce_problem* problem, mce_result* result) {
+    if (!c) return fail(MCE_ERR_ARG, "ctx is NULL");
+    if (!result) return fail(MCE_ERR_ARG, "result is NULL");
+    if (!result->logE && !((problem ? problem->flags : 0) & MCE_FLAG_PARTIALS))
+        return fail(MCE_ERR_ARG, "result.logE is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    Run r{problem, true, 0, nullptr, nullptr, result, nullptr};
+    return run_problem(c, r);
+}
+
+int mce_evidence_batch(mce_ctx* c, int n, const mce_problem* problems, mce_result* results) {
+    if (!c) return fail(MCE_ERR_ARG, "ctx is NULL");
+    if (n < 0 || (n > 0 && (!problems || !results))) return fail(MCE_ERR_ARG, "bad batch arguments");
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int i = 0; i < n; ++i) {
+        if (!results[i].logE) return fail(MCE_ERR_ARG, "results[%d].logE is NULL", i);
+        Run r{&problems[i], true, 0, nullptr, nullptr, &results[i], nullptr};
+        const int rc = run_problem(c, r);
+        if (rc) {
+            char tmp[sizeof(g_err)];
+            snprintf(tmp, sizeof(tmp), "%s", g_err);
+            return fail(rc, "problem %d: %s", i, tmp);
+        }
+    }
+    return MCE_OK;
+}
+
+int mce_knn(mce_ctx* c, const mce_problem* problem, int n_neighbors, double* dknn, int64_t* idx, mce_stats* stats) {
+    if (!c) return fail(MCE_ERR_ARG, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    Run r{problem, false, n_neighbors, dknn, idx, nullptr, stats};
+    if (problem && !problem->W) {
+        // whitening estimated from the data, as in mce_evidence
+    }
+    return run_problem(c, r);
+}
+
+int mce_combine_partials(int nparts, int nk, const double* parts, double* out) {
+    if (nparts < 1 || nk < 1 || !parts || !out) return fail(MCE_ERR_ARG, "bad arguments to mce_combine_partials");
+    for (int k = 0; k < nk; ++k) {
+        double m = -INFINITY;
+        for (int i = 0; i < nparts; ++i) {
+            const double v = parts[((size_t)i * nk + k) * 3];
+            if (v > m || isnan(v)) m = v;
+        }
+        double s1 = 0.0, s2 = 0.0;
+        for (int i = 0; i < nparts; ++i) {
+            const double* t = parts + ((size_t)i * nk + k) * 3;
+            if (t[0] == -INFINITY) continue;
+            const double f = exp(t[0] - m);
+            s1 += t[1] * f;
+            s2 += t[2] * f * f;
+        }
+        out[k * 3] = m;
+        out[k * 3 + 1] = s1;
+        out[k * 3 + 2] = s2;
+    }
+    return MCE_OK;
+}
+
+int mce_finalize(const double* partials, int nk, int d, int cross, int64_t n_query_total, double log_sum_w,
+                 double log_jacobian, double log_prior_volume, double* logE, double* var_logE) {
+    if (!partials || !logE || nk < 1 || d < 1) return fail(MCE_ERR_ARG, "bad arguments to mce_finalize");
+    const double logc = 0.5 * d * log(M_PI) - lgamma(1.0 + 0.5 * d);  // log(pi^{d/2} / Gamma(1 + d/2)), MCEvidence.py:1110
+    for (int k = 1; k <= nk; ++k) {
+        const double* t = partials + (size_t)(k - 1) * 3;
+        const int k_nn = cross ? k + 1 : k;                              // MCEvidence.py:1120-1122
+        logE[k - 1] = log_sum_w + log_jacobian - log_prior_volume - log((double)n_query_total * k_nn + 1.0) + logc +
+                      t[0] + log(t[1]);                                  // MCEvidence.py:1123-1131
+        if (var_logE) var_logE[k - 1] = t[2] / (t[1] * t[1]) - 1.0 / (double)n_query_total;
+    }
+    return MCE_OK;
+}
+
+int mce_fma_peak(mce_ctx* c, int variant, int iters, double* tflops, double* ms_out) {
+    if (!c || !tflops) return fail(MCE_ERR_ARG, "ctx or tflops is NULL");
+    if (variant < 0 || variant > 1 || iters < 1) return fail(MCE_ERR_ARG, "bad variant/iters");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    const int grid = c->sm_count * 8;
+    int rc = c->sink.ensure((size_t)grid * 256 * sizeof(float));
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    launch_fma_peak(variant, iters / 8 + 1, grid, c->sink.as<float>(), st);  // warm-up
+    CU(cudaEventRecord(c->ev[EV_START], st));
+    launch_fma_peak(variant, iters, grid, c->sink.as<float>(), st);
+    CU(cudaEventRecord(c->ev[EV_END], st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, c->ev[EV_START], c->ev[EV_END]));
+    *tflops = (double)fma_peak_flops(variant, iters, grid) / ((double)ms * 1e-3) / 1e12;
+    if (ms_out) *ms_out = ms;
+    return MCE_OK;
+}
+
+}  // extern "C"

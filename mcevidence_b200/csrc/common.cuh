@@ -1,0 +1,116 @@
+// Shared declarations of the kNN-evidence kernels (sm_100a).
+//
+// Data layout in HBM (per problem, all owned by the context workspace):
+//   X      raw samples, FP64, (n, ld) row-major as handed over by the caller
+//   Y64    whitened samples, FP64, (n, d) row-major (rows are gathered by the re-rank)
+//   TILES  whitened reference set for the filter, FP32, one contiguous block per tile of
+//          TILE_REFS reference rows: (d+1) rows of TILE_REFS floats, row c < d holds
+//          coordinate c, row d holds h_j = -|y_j|^2/2.  A tile is one TMA bulk copy.
+//   CAND   candidate indices int32 [ref_chunks][list_len][nq_pad] and final thresholds
+//          float [ref_chunks][nq_pad] written by the filter, read by the re-rank
+//   DKNN   FP64 (nq, K) ascending neighbour distances, IDX int64 (nq, K)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mce {
+
+constexpr int TILE_REFS = 128;        // reference rows per TMA tile
+constexpr int FILTER_THREADS = 128;   // threads per filter CTA (4 warps)
+constexpr int FILTER_STAGES = 4;      // TMA ring depth
+constexpr int KCAP = 16;              // == MCE_MAX_NEIGHBOURS
+constexpr int MAX_DIM = 64;           // == MCE_MAX_DIM
+
+struct Segment {            // one strided FP64 sample array
+    const double* x;
+    long long n;
+    long long ld;
+};
+
+// ---- K0: covariance, Cholesky, whitening matrix -------------------------------------------
+struct CovWorkspace {
+    double* partial;        // [cov_grid][max(d, npairs)]
+    double* mean;           // [d]
+    double* W;              // [d*d]  y = (x - mean) W,  W = L^{-T}
+    double* logj;           // [1]    0.5 log det C
+    int*    status;         // [1]    0 ok, 1 not positive definite
+};
+int cov_grid_size(int sm_count);
+void launch_covariance(const Segment& a, const Segment& b, int d, const CovWorkspace& ws, int grid,
+                       cudaStream_t st, int* launches);
+
+// ---- K1: whitening on load ------------------------------------------------------------------
+// Writes Y64 rows [0, n) and, when tiles != nullptr, the FP32 tiles (padding rows of the last
+// tile get coordinates 0 and h = -inf) and atomically maxes *rmax_bits with |y| rounded up.
+void launch_whiten(const Segment& x, int d, const double* W, const double* mu, double* y64,
+                   float* tiles, unsigned int* rmax_bits, cudaStream_t st, int* launches);
+
+// ---- K2: tiled FP32 filter ------------------------------------------------------------------
+struct FilterParams {
+    const double* yq;        // whitened queries FP64 (row r at yq + r*d); rows [q_begin, q_end) are searched
+    const float*  tiles;     // reference tiles
+    int*   cand_idx;         // [ref_chunks][list_len][nq_pad]
+    float* cand_th;          // [ref_chunks][nq_pad]
+    long long q_begin, q_end;
+    long long nq_pad;
+    long long self_offset;   // auto mode: reference index of query row r is r + self_offset; cross mode: any
+    int self_exclude;        // 1 in auto mode
+    int ntiles;
+    int tiles_per_chunk;
+    int ref_chunks;
+    int nqblocks;
+    int list_len;
+    int d;
+};
+struct FilterConfig { int tq, tr, packed; };
+// Returns 0 and fills grid/smem/ctas_per_sm on success, -1 if (d, cfg) has no instantiation.
+int filter_query(int d, const FilterConfig& cfg, int list_len, int* queries_per_cta, int* smem_bytes,
+                 int* ctas_per_sm);
+int launch_filter(const FilterParams& p, const FilterConfig& cfg, cudaStream_t st, int* launches);
+void filter_default_config(int d, int list_len, FilterConfig* cfg);
+
+// ---- K3: FP64 re-rank + verification, exact re-scan ---------------------------------------
+struct RerankParams {
+    const double* yq;        // whitened queries
+    const double* yr;        // whitened references
+    const int*   cand_idx;
+    const float* cand_th;
+    const unsigned int* rmax_bits;
+    double*    dknn;         // (nq, out_ld) ; neighbours written at column out_col0..
+    long long* idx;
+    int* flagged;            // [nq] local row ids needing an exact re-scan
+    int* nflagged;
+    long long q_begin, q_end, nq_pad;
+    long long n_ref;
+    long long self_offset;
+    int self_exclude;
+    int ref_chunks, list_len;
+    int d, k;                // k true neighbours wanted
+    int out_ld, out_col0;    // output row stride and first column (1 when a synthetic self column is kept)
+    int write_self_col;      // write (0.0, own index) into column 0
+    int flag_all;            // MCE_FLAG_EXACT_ONLY: flag every row
+};
+void launch_rerank(const RerankParams& p, cudaStream_t st, int* launches);
+void launch_exact_rescan(const RerankParams& p, int grid, cudaStream_t st, int* launches);
+
+// ---- K4: log-volume + logsumexp epilogue ---------------------------------------------------
+struct ReduceParams {
+    const double* dknn;      // (nq, ld) neighbour distances; neighbour i (1-based) at column col0 + i - 1
+    const double* logl;      // indexed by global query row
+    const double* weights;
+    double* block_partial;   // [grid][nk][3]
+    double* out;             // [nk][3]  (max, sum, sum2)
+    long long q_begin, q_end;
+    int ld, col0;
+    int first_nb;            // neighbour used by output 0: 1 (auto) or 2 (cross)
+    int nk;                  // kmax - 1 outputs
+    int d;
+};
+int reduce_grid_size(long long nq);
+void launch_reduce(const ReduceParams& p, int grid, cudaStream_t st, int* launches);
+
+// ---- FP32 FMA microbenchmark ----------------------------------------------------------------
+void launch_fma_peak(int variant, int iters, int grid, float* sink, cudaStream_t st);
+long long fma_peak_flops(int variant, int iters, int grid);
+
+}  // namespace mce
