@@ -233,9 +233,42 @@ class Context:
         _check(self._lib, self._lib.mce_knn(self._h, C.byref(p), int(n_neighbors), _ptr(dknn), _ptr(idx), C.byref(st)))
         return dknn, idx, st.as_dict()
 
-    def evidence_device(self, problem, result):
-        """Raw call with a caller-filled ``Problem`` (device pointers) and ``Result``."""
-        _check(self._lib, self._lib.mce_evidence(self._h, C.byref(problem), C.byref(result)))
+    def evidence_device(self, query_ptr, n_query, ld_query, logl_ptr, weights_ptr, ndim, kmax, ref_ptr=0,
+                        n_ref=0, ld_ref=0, q_range=None, log_sum_w=0.0, log_prior_volume=0.0, W=None, W_ref=None,
+                        mu=None, log_jacobian=0.0, want_partials=False, want_logE=True, exact_only=False):
+        """``mce_evidence`` on DEVICE pointers (integers, e.g. ``tensor.data_ptr()``) that live on this
+        context's device; nothing is copied host<->device except the few result scalars.  Used for the
+        resident-input benchmark and by the row-sharded multi-GPU path (``mcevidence_b200.dist``)."""
+        keep = []
+        p = Problem()
+        p.query, p.n_query, p.ld_query = int(query_ptr), int(n_query), int(ld_query)
+        if ref_ptr:
+            p.ref, p.n_ref, p.ld_ref = int(ref_ptr), int(n_ref), int(ld_ref)
+        p.logl, p.weights = int(logl_ptr), int(weights_ptr)
+        if q_range is not None:
+            p.q_begin, p.q_end = int(q_range[0]), int(q_range[1])
+        p.d, p.kmax = int(ndim), int(kmax)
+        p.flags = FLAG_DEVICE_PTRS | (FLAG_PARTIALS if want_partials else 0) | (FLAG_EXACT_ONLY if exact_only else 0)
+        for name, arr, shape in (('W', W, (ndim, ndim)), ('W_ref', W_ref, (ndim, ndim)), ('mu', mu, (ndim,))):
+            if arr is not None:
+                arr = np.ascontiguousarray(arr, dtype=np.float64)
+                if arr.shape != shape:
+                    raise ValueError('%s must have shape %s' % (name, shape))
+                keep.append(arr)
+                setattr(p, name, _ptr(arr))
+        p.log_jacobian, p.log_sum_w, p.log_prior_volume = float(log_jacobian), float(log_sum_w), float(log_prior_volume)
+        kk = max(2, int(kmax))
+        r = Result()
+        out = {}
+        if want_logE:
+            out['logE'], out['var_logE'] = np.empty(kk - 1), np.empty(kk - 1)
+            r.logE, r.var_logE = _ptr(out['logE']), _ptr(out['var_logE'])
+        if want_partials:
+            out['partials'] = np.empty((kk - 1, 3))
+            r.partials = _ptr(out['partials'])
+        _check(self._lib, self._lib.mce_evidence(self._h, C.byref(p), C.byref(r)))
+        out.update({'log_jacobian': r.log_jacobian, 'stats': r.stats.as_dict()})
+        return out
 
     def fma_peak(self, variant=1, iters=4096):
         tf, ms = C.c_double(), C.c_double()

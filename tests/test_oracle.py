@@ -1,0 +1,94 @@
+"""The CPU oracle against the frozen outputs of the unmodified reference (tests/golden)."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import mce_oracle as O
+from conftest import Golden
+
+
+def partitions(g):
+    """Rebuild the s1 / s2 arrays the reference built, replaying its global-RNG calls."""
+    from mcevidence_b200.chains import MCSamples
+    from collections import namedtuple
+    sv = namedtuple('split_var', 'split frac shuffle')
+    np.random.seed(g.np_seed)
+    chains = [c.copy() for c in g.chains]
+    if g.as_files:
+        # burn-in / thinning only apply to file input in the reference: replay them through the
+        # host-side chain container (its parity with the reference is checked in test_chains.py)
+        ms = MCSamples.__new__(MCSamples)
+        ms.debug, ms.px = False, 'x'
+        ms.split, ms.s1frac, ms.shuffle = g.ctor.get('split', False), g.ctor.get('s1frac', 0.5), True
+        import logging
+        ms.logger = logging.getLogger('test')
+        ms.iw, ms.ilike, ms.itheta = 0, 1, 2
+        ms.chains = chains
+        data = ms.chains2samples(burnlen=g.ctor.get('burnlen', 0), thinlen=g.ctor.get('thinlen', 0))
+    else:
+        ms = MCSamples(chains, csplit=sv(g.ctor.get('split', False), g.ctor.get('s1frac', 0.5), True),
+                       log_level=30)
+        data = ms.data
+    return data['s1'], data['s2']
+
+
+@pytest.mark.parametrize('knn', ['sklearn', 'brute'])
+def test_oracle_reproduces_reference(golden, knn):
+    g = golden
+    s1, s2 = partitions(g)
+    np.testing.assert_array_equal(s1.samples[:, 0], g.raw['s1_col0'])
+    np.testing.assert_array_equal(s1.weights, g.raw['s1_weights'])
+    logl = -s1.loglikes
+    if g.ev.get('pos_lnp'):
+        logl = -logl
+    pv = g.ev.get('pvolume', g.ctor.get('priorvolume', 1.0))
+    mle, parts = O.evidence(s1.samples, logl, s1.weights, g.ndim, g.ctor.get('kmax', 5),
+                            s2=None if s2.samples is None else s2.samples, priorvolume=pv, knn=knn,
+                            return_parts=True)
+    assert mle.shape == g.mle.shape
+    # the restatement follows the reference line by line: same summation order, same library calls
+    tol = 0.0 if knn == 'sklearn' else 1e-9
+    assert np.abs(mle - g.mle).max() <= tol
+    if 'dknn' in g.raw.files:
+        ref_d, ref_i = g.raw['dknn'], g.raw['idx']
+        if knn == 'sklearn':
+            np.testing.assert_array_equal(parts['dknn'], ref_d)
+        else:
+            np.testing.assert_allclose(parts['dknn'], ref_d, rtol=1e-12, atol=0)
+            # indices agree wherever the reference has no exact tie
+            assert (parts['idx'] != ref_i).sum() == 0
+
+
+def test_log_space_form_equals_linear_form(golden):
+    g = golden
+    s1, s2 = partitions(g)
+    logl = -s1.loglikes
+    mle, parts = O.evidence(s1.samples, logl, s1.weights, g.ndim, g.kmax, s2=s2.samples, knn='brute',
+                            return_parts=True)
+    k0 = parts['k0']
+    mlog, var = O.evidence_from_dknn_log(parts['dknn'], logl, s1.weights, g.ndim, g.kmax, k0, parts['sum_w'],
+                                         math.log(parts['cov']['J']), 0.0)
+    assert np.abs(mlog[1:] - mle).max() < 5e-12
+    assert np.all(var[1:] > 0) and np.all(var[1:] < 1.0)
+
+
+def test_brute_knn_order_and_ties():
+    rng = np.random.default_rng(0)
+    base = rng.normal(size=(40, 3))
+    x = np.repeat(base, 3, axis=0)            # every point three times: exact ties at distance 0
+    d, i = O.knn_brute_fp64(x, x, 4, exclude_self=True)
+    assert np.all(d[:, :2] == 0.0) and np.all(d[:, 2] > 0)
+    assert np.all(np.diff(d, axis=1) >= 0)
+    rows = np.arange(len(x))
+    assert not np.any(i == rows[:, None])
+    # ties ordered by index
+    assert np.all(i[:, 0] < i[:, 1])
+    dsk, isk = O.knn_sklearn(x, x, 5)
+    np.testing.assert_allclose(dsk[:, 1:], d, rtol=1e-12, atol=1e-300)
+
+
+def test_unit_ball_constant():
+    import scipy.special as sp
+    for d in (1, 2, 3, 10, 27):
+        assert abs(O.log_unit_ball_volume(d) - math.log(math.pi ** (d / 2) / sp.gamma(1 + d / 2))) < 1e-12
