@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""Benchmark of the kNN-evidence hot path (BASELINE.json metric) -- one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one pass of the hot path (covariance -> whitening -> exact k-th nearest neighbours ->
+log-volume reduction -> per-k logE) over one synthetic chain.  Default workload: BASELINE cfg2,
+synthetic correlated Gaussian chain N=1e6, d=10, kmax=4, auto mode.
+
+* ``value``  pair-distances/s with the chain already resident in HBM, timed with CUDA events on the
+  launching stream, max over ranks (query rows are sharded over ranks: strong scaling).
+* ``e2e``    the same metric through the public host API (``Context.evidence`` /
+  ``dist.evidence_sharded``): pinned host arrays in, logE out, copies inside the timed region.
+* ``roofline``  the dominant kernel (K2 filter) against the FP32 FMA pipe, whose peak is measured in
+  this run with an FMA microbenchmark (MEASURED_PEAKS.json has HBM and tensor peaks only).
+* ``cpu_baseline``  the oracle port of the reference path (sklearn, all host cores) on a bounded
+  sample; ``--impl reference`` times the same port as its own arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n, d, kmax, cross, description)
+    'cfg2': (1000000, 10, 4, False, 'cfg2: synthetic correlated Gaussian chain N=1e6 d=10 kmax=4 auto'),
+    'cfg3': (1000000, 27, 4, True, 'cfg3: cross evidence d=27, 2e6 rows split 1e6/1e6, kmax=4'),
+    'cfg5': (16000000, 20, 8, False, 'cfg5: N=1.6e7 d=20 kmax=8 auto (scaling run)'),
+    'cfg5s': (2000000, 20, 8, False, 'cfg5 shape at N=2e6 d=20 kmax=8 auto'),
+    'small': (100000, 10, 4, False, 'N=1e5 d=10 kmax=4 auto'),
+}
+FP32_PEAK_THEORETICAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.4: SMs x lanes x 2 FLOP x max clock
+METRIC = 'knn_pair_dists_per_s'
+UNIT = 'pair-dists/s'
+
+
+def make_workload(name, seed=0):
+    from mcevidence_b200.synthetic import gaussian_chain
+    n, d, kmax, cross, desc = WORKLOADS[name]
+    chain, info = gaussian_chain(n * (2 if cross else 1), d, seed=seed)
+    s = np.ascontiguousarray(chain[:, 2:])
+    logl, w = -chain[:, 1], np.ascontiguousarray(chain[:, 0])
+    if cross:
+        return dict(s1=s[:n], s2=s[n:], logl=logl[:n], w=w[:n], d=d, kmax=kmax, cross=True, desc=desc, lnZ=info['lnZ'])
+    return dict(s1=s, s2=None, logl=logl, w=w, d=d, kmax=kmax, cross=False, desc=desc, lnZ=info['lnZ'])
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    FIELDS = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+              'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix='mce_clocks_', suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.FIELDS,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, smax, power, reasons = [], [], [], set()
+        try:
+            for line in open(self.path):
+                t = [x.strip() for x in line.split(',')]
+                if len(t) < 9:
+                    continue
+                try:
+                    sm.append(float(t[1])); smax.append(float(t[2])); power.append(float(t[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), t[5:9]):
+                    if val.lower().startswith('active'):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            pw = np.array(power)
+            load = np.array(sm)[pw >= 0.5 * pw.max()] if pw.max() > 0 else np.array(sm)
+            out.update({'sm_mhz': float(np.median(load)), 'sm_max_mhz': float(max(smax)), 'reasons': sorted(reasons),
+                        'samples': len(sm), 'power_w_max': float(pw.max())})
+        return out
+
+
+def host_info():
+    model = ''
+    try:
+        for line in open('/proc/cpuinfo'):
+            if line.startswith('model name'):
+                model = line.split(':', 1)[1].strip()
+                break
+    except Exception:
+        pass
+    import sklearn
+    import scipy
+    return {'cores': os.cpu_count(), 'cpu_model': model, 'sklearn': sklearn.__version__, 'numpy': np.__version__,
+            'scipy': scipy.__version__}
+
+
+def cpu_port_once(wl, n_s):
+    """One run of the oracle port of the reference path (sklearn, n_jobs=-1, scalar volume loop as in
+    MCEvidence.py:1108-1110) on the first n_s rows of the workload.  Returns (seconds, logE)."""
+    from oracle import mce_oracle as O
+    s1, logl, w = wl['s1'][:n_s], wl['logl'][:n_s], wl['w'][:n_s]
+    s2 = wl['s2'][:n_s] if wl['cross'] else None
+    t = time.perf_counter()
+    mle = O.evidence(s1, logl, w, wl['d'], wl['kmax'], s2=s2, knn='sklearn', n_jobs=-1, scalar_loop=True)
+    return time.perf_counter() - t, mle
+
+
+def pick_cpu_sample(wl, target_s, n_full):
+    """Calibrate on a small sample, then size the sample for ~target_s seconds of CPU work."""
+    n0 = min(20000, n_full)
+    t0, _ = cpu_port_once(wl, n0)
+    expo = 1.3 if wl['d'] <= 15 else 2.0          # kd_tree ~N^1.3, brute N^2
+    n_s = int(n0 * (target_s / max(t0, 1e-3)) ** (1.0 / expo))
+    return int(max(n0, min(n_full, n_s))), expo
+
+
+def cpu_baseline(wl, target_s=20.0):
+    n_full = len(wl['s1'])
+    n_s, expo = pick_cpu_sample(wl, target_s, n_full)
+    t, _ = cpu_port_once(wl, n_s)
+    hi = host_info()
+    algo = 'kd_tree' if wl['d'] <= 15 else 'brute'
+    val = float(n_s) * float(n_s) / t
+    return {'value': val, 'unit': UNIT, 'cores': hi['cores'], 'kind': 'port',
+            'sample': 'first %d of %d rows of the same chain, whole evidence() port, sklearn %s (%s), n_jobs=-1: %.2f s; '
+                      'pair-equivalents = N_s^2/t. Cost grows ~N^%.1f, so at full N the CPU figure would be '
+                      '~(N/N_s)^%.1f = %.1fx higher (%.0f s per logE extrapolated)' % (
+                          n_s, n_full, hi['sklearn'], algo, t, expo, 2 - expo, (n_full / n_s) ** (2 - expo),
+                          t * (n_full / n_s) ** expo),
+            'seconds': t, 'n_sample': n_s, 'cpu_model': hi['cpu_model'],
+            's_per_logE_full_extrapolated': t * (n_full / n_s) ** expo}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle port: numpy + sklearn exactly as
+    MCEvidence.py:1033-1131 calls them) on the host cores, rank 0 only."""
+    if rank != 0:
+        return 0
+    wl = make_workload(args.workload)
+    n_full = len(wl['s1'])
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    n_s, expo = pick_cpu_sample(wl, min(25.0, budget), n_full)
+    for _ in range(args.warmup):
+        cpu_port_once(wl, n_s)
+    times = []
+    for _ in range(args.steps):
+        t, mle = cpu_port_once(wl, n_s)
+        times.append(t)
+    tt = float(np.sum(times))
+    hi = host_info()
+    val = args.steps * float(n_s) * float(n_s) / tt
+    sample = ('first %d of %d rows per step, oracle port of MCEvidence.evidence() (sklearn %s, %s, n_jobs=-1, %d cores); '
+              'cost ~N^%.1f so full-size pair-equivalents/s would be ~%.1fx higher' % (
+                  n_s, n_full, hi['sklearn'], 'kd_tree' if wl['d'] <= 15 else 'brute', hi['cores'], expo,
+                  (n_full / n_s) ** (2 - expo)))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * tt / args.steps, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': wl['desc'], 'sample_rows': n_s},
+            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': hi['cores'], 'kind': 'port', 'sample': sample,
+                             'cpu_model': hi['cpu_model']},
+            'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            's_per_logE_full_extrapolated': (tt / args.steps) * (n_full / n_s) ** expo,
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-seconds', type=float, default=20.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        return run_reference_arm(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from mcevidence_b200 import _lib
+    from mcevidence_b200.dist import evidence_sharded, shard_range
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=device)
+    ctx = _lib.default_context(local_rank)
+    stream = torch.cuda.current_stream(device)
+    ctx.set_stream(stream.cuda_stream)
+
+    wl = make_workload(args.workload) if rank == 0 else None
+    meta = [None]
+    if rank == 0:
+        meta = [{k: wl[k] for k in ('d', 'kmax', 'cross', 'desc', 'lnZ')}]
+        meta[0]['n'] = len(wl['s1'])
+        meta[0]['n_ref'] = len(wl['s2']) if wl['cross'] else len(wl['s1'])
+        meta[0]['sum_w'] = float(wl['w'].sum())
+    if world > 1:
+        dist.broadcast_object_list(meta, src=0)
+    m = meta[0]
+    n, n_ref, d, kmax, cross, sum_w = m['n'], m['n_ref'], m['d'], m['kmax'], m['cross'], m['sum_w']
+
+    # ---- pinned host copies (rank 0) and resident device copies (every rank) ------------------
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+    host = {}
+    if rank == 0:
+        host = {'samples': pinned(wl['s1']), 'logl': pinned(wl['logl']), 'weights': pinned(wl['w'])}
+        if cross:
+            host['ref'] = pinned(wl['s2'])
+    res = {}
+    for key, shape in (('samples', (n, d)), ('logl', (n,)), ('weights', (n,))) + ((('ref', (n_ref, d)),) if cross else ()):
+        t = host[key].to(device, non_blocking=True) if rank == 0 else torch.empty(shape, dtype=torch.float64, device=device)
+        if world > 1:
+            dist.broadcast(t, src=0)
+        res[key] = t
+    torch.cuda.synchronize(device)
+
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=device)   # > 126 MB L2
+
+    def step_resident():
+        if world == 1:
+            r = res.get('ref')
+            return ctx.evidence_device(res['samples'].data_ptr(), n, d, res['logl'].data_ptr(), res['weights'].data_ptr(),
+                                       d, kmax, ref_ptr=r.data_ptr() if cross else 0, n_ref=n_ref, ld_ref=d,
+                                       log_sum_w=math.log(sum_w))
+        return evidence_sharded(None, None, None, kmax, resident=res, sum_w=sum_w, ctx=ctx, device=device)
+
+    def step_e2e():
+        if world == 1:
+            return ctx.evidence(host['samples'].numpy(), host['logl'].numpy(), host['weights'].numpy(), kmax,
+                                ref=host['ref'].numpy() if cross else None, ndim=d, log_sum_w=math.log(sum_w))
+        if rank == 0:
+            return evidence_sharded(host['samples'].numpy(), host['logl'].numpy(), host['weights'].numpy(), kmax,
+                                    ref=host['ref'].numpy() if cross else None, ndim=d, sum_w=sum_w, ctx=ctx, device=device)
+        return evidence_sharded(None, None, None, kmax, ctx=ctx, device=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    # ---- FP32 FMA peak, measured live ----------------------------------------------------------
+    peak = {}
+    for variant, name in ((0, 'ffma'), (1, 'ffma2')):
+        peak[name] = max(ctx.fma_peak(variant, 8192)[0] for _ in range(3))
+    fma_peak = max(peak.values())
+
+    # ---- value: inputs resident, CUDA events on the launching stream --------------------------
+    for _ in range(args.warmup):
+        out = step_resident()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches, ms_filter, rescanned, stats = 0, [], 0, None
+    for i in range(args.steps):
+        flush.zero_()                                  # L2 flush between timed iterations (not timed)
+        ev[i][0].record(stream)
+        out = step_resident()
+        ev[i][1].record(stream)
+        stats = out['stats']
+        launches += stats['launches'] + (2 if world > 1 else 0)
+        ms_filter.append(stats['ms_filter'])
+        rescanned += stats['rows_rescanned']
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = sum(a.elapsed_time(b) for a, b in ev)
+    tmax = torch.tensor([t_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    t_ms = float(tmax.item())
+    loge = out['logE']
+    pairs_total = float(n) * float(n_ref)
+    value = args.steps * pairs_total / (t_ms * 1e-3)
+
+    # ---- e2e: public host API, pinned host arrays in, logE out --------------------------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oe = step_e2e()
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    te = float(te.item())
+    h2d = (n * d + 2 * n + (n_ref * d if cross else 0)) * 8
+    d2h = (kmax - 1) * 3 * 8 + 160
+    e2e_value = args.steps * pairs_total / te
+
+    if rank == 0:
+        lo, hi = shard_range(n, 0, world)
+        pairs_launch = float(hi - lo) * float(n_ref)                    # units one K2 launch processes on rank 0
+        t_k2 = float(np.mean(ms_filter)) * 1e-3
+        achieved = 3.0 * d * pairs_launch / t_k2 / 1e12                 # algorithmic: 3d FLOP per pair (sub, mul, add)
+        roofline = {'bound': 'fp32_fma', 'achieved': achieved, 'peak': fma_peak, 'unit': 'TFLOP/s',
+                    'frac': achieved / fma_peak, 'traffic': None,
+                    'kernel': 'knn_filter_kernel<D=%d,TQ=%d,TR=%d,packed=%d>' % (d, stats['filter_tq'], stats['filter_tr'],
+                                                                              stats['filter_packed']),
+                    'ms_per_launch': 1e3 * t_k2, 'share_of_step': float(np.sum(ms_filter)) / t_ms if world == 1 else None,
+                    'peak_source': 'FMA microbenchmark in this run (mce_fma_peak): ffma %.1f, ffma2 %.1f TFLOP/s at 2 FLOP per '
+                                   'lane-FMA; theoretical %.1f' % (peak['ffma'], peak['ffma2'], FP32_PEAK_THEORETICAL_TFLOPS),
+                    'frac_theoretical': achieved / FP32_PEAK_THEORETICAL_TFLOPS,
+                    'fma_pipe_frac': (2.0 * d * pairs_launch / t_k2 / 1e12) / fma_peak,
+                    'note': 'the filter issues d FMAs per pair (2d executed FLOP) for the 3d algorithmic FLOP of the '
+                            'difference form, so frac can exceed 1; fma_pipe_frac is executed FMA rate / measured FMA peak'}
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': t_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+                'dtype': 'f32 filter, f64 re-rank/reduce', 'data': 'synthetic',
+                'config': {'workload': m['desc'], 'n': n, 'n_ref': n_ref, 'ndim': d, 'kmax': kmax, 'mode': 'cross' if cross else 'auto',
+                           'parallelism': 'query rows sharded over %d GPU(s), reference set replicated' % world,
+                           'l2': '512 MiB memset between timed steps (not timed); working set > L2'},
+                'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                        's_per_logE': te / args.steps},
+                'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline,
+                's_per_logE': t_ms * 1e-3 / args.steps, 'logE': [float(x) for x in loge],
+                'logE_minus_analytic': [float(x - m['lnZ']) for x in loge], 'rows_rescanned_per_step': rescanned / args.steps,
+                'stage_ms': {k: stats[k] for k in ('ms_cov', 'ms_whiten', 'ms_filter', 'ms_rerank', 'ms_exact', 'ms_reduce')},
+                'filter': {k: stats[k] for k in ('filter_tq', 'filter_tr', 'filter_packed', 'ref_chunks', 'list_len',
+                                                 'filter_grid', 'filter_smem', 'filter_ctas_per_sm')}}
+        if world == 1 and not args.no_cpu_baseline:
+            line['cpu_baseline'] = cpu_baseline(wl, args.cpu_seconds)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

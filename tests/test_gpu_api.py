@@ -1,0 +1,92 @@
+"""The drop-in Python API and command line on the GPU: same calls a user of the reference makes."""
+import math
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import MCEvidence as M
+from oracle import mce_oracle as O
+from mcevidence_b200.synthetic import gaussian_chain, write_cosmomc_root
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cli_on_cosmomc_root(tmp_path):
+    """BASELINE config 1 shape: `MCEvidence.py <root> -k 2 --burn 0.3` (and the -b alias) on a
+    CosmoMC-format root (4 chain files + .ranges), cosmological parameters only."""
+    root = str(tmp_path / 'base_plikHM_TT_lowTEB')
+    names, vol = write_cosmomc_root(root, nchains=4, nrows=1500, seed=3)
+    chains = [np.loadtxt('%s_%d.txt' % (root, i + 1)) for i in range(4)]
+    burned = np.concatenate([c[int(len(c) * 0.3):] for c in chains])
+    want = O.evidence(burned[:, 2:], -burned[:, 1], burned[:, 0], 6, 2, priorvolume=vol, knn='brute')
+    got = M.main([root, '-k', '2', '--burn', '0.3', '-vb', '0'])
+    assert got.shape == (1,) and abs(got[0] - want[0]) < 1e-9
+    got_alias = M.main([root, '-k', '2', '-b', '0.3', '-vb', '0'])
+    assert got_alias[0] == got[0]
+    # --allparams uses every varied column; -ic picks one chain file
+    burned1 = chains[1][int(len(chains[1]) * 0.3):]
+    want_all = O.evidence(burned1[:, 2:], -burned1[:, 1], burned1[:, 0], len(names), 3,
+                          priorvolume=24.0 ** len(names), knn='brute')
+    got_all = M.main([root, '-k', '3', '--burn', '0.3', '--allparams', '-ic', '2', '-vb', '0'])
+    assert np.abs(got_all - want_all).max() < 1e-9
+    # as a script
+    p = subprocess.run([sys.executable, os.path.join(ROOT, 'MCEvidence.py'), root, '-k', '2', '--burn', '0.3'],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    assert 'ln(B)[k=1] = ' in p.stderr + p.stdout
+    logged = float((p.stderr + p.stdout).split('ln(B)[k=1] = ')[1].split()[0])
+    assert abs(logged - want[0]) < 1e-9
+
+
+def test_cross_mode_through_class():
+    c, _ = gaussian_chain(6000, 7, seed=21, nextra=3)
+    np.random.seed(77)
+    m = M.MCEvidence([c], split=True, kmax=4, ndim=7, priorvolume=4.0, verbose=0)
+    got = m.evidence()
+    np.random.seed(77)
+    n = len(c)
+    ix = np.random.choice(range(n), size=int(n * 0.5), replace=False)
+    nix = np.setxor1d(range(n), ix)
+    want = O.evidence(c[ix, 2:], -c[ix, 1], c[ix, 0], 7, 4, s2=c[nix, 2:], priorvolume=4.0, knn='brute')
+    assert np.abs(got - want).max() < 1e-9
+    assert m.nsample == [3000, 3000]
+
+
+def test_batches_and_info():
+    c, _ = gaussian_chain(3000, 5, seed=22)
+    m = M.MCEvidence([c], kmax=3, verbose=0, nbatch=3, brange=[2.5, 3.4], bscale='logpower')
+    res, info = m.evidence(info=True)
+    assert res.shape == (3, 2) and info['Nsamples'] == '3000'
+    cs = O.covariance_stats(c[:, 2:])
+    for i, p in enumerate(np.linspace(2.5, 3.4, 3)):
+        S = int(10 ** p)
+        y = O.whiten(c[:S, 2:], cs['eVec'], cs['eVal'])
+        d, _ = O.knn_brute_fp64(y, y, 3, exclude_self=True)
+        dk = np.concatenate((np.zeros((S, 1)), d), axis=1)
+        want = O.evidence_from_dknn_linear(dk, -c[:S, 1], c[:S, 0], 5, 3, 1, c[:, 0].sum(), cs['J'], 0.0)[1:]
+        assert np.abs(res[i] - want).max() < 1e-9
+
+
+def test_importance_sampling_hook():
+    """isfunc rescales adjusted_weights only -> SumW (MCEvidence.py:265-270, 1126; planck_mcevidence.py:344)."""
+    c, _ = gaussian_chain(2000, 4, seed=23)
+    f = lambda s: 0.5 * ((s[:, 0] - 0.1) / 2.0) ** 2
+    a = M.MCEvidence([c], kmax=2, verbose=0).evidence()
+    b = M.MCEvidence([c], kmax=2, verbose=0, isfunc=f).evidence()
+    aw = c[:, 0] * np.exp(-f(c[:, 2:]))
+    assert abs((b - a)[0] - (math.log(aw.sum()) - math.log(c[:, 0].sum()))) < 1e-10
+
+
+def test_grid_of_chains_batched():
+    """Chain-per-GPU batching (planck grid shape): many small independent problems."""
+    from mcevidence_b200.grid import evidence_many
+    chains = [gaussian_chain(n, d, seed=30 + i, integer_weights=True, inflate=1.0)[0]
+              for i, (n, d) in enumerate([(1475, 6), (5917, 7), (3000, 8), (2200, 9), (4000, 7)])]
+    loge, var, ms = evidence_many(chains, kmax=2)
+    for c, le in zip(chains, loge):
+        want = O.evidence(c[:, 2:], -c[:, 1], c[:, 0], c.shape[1] - 2, 2, knn='brute')
+        assert np.abs(le - want).max() < 1e-9

@@ -1,0 +1,260 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the frozen reference outputs.
+
+Tolerances.  Neighbour indices and distances on identical coordinates (identity whitening): bit-exact.
+Whitened pipeline: r_k within 1e-12 relative of the exact FP64 oracle, logE within 1e-6 absolute of
+the reference (the north-star tolerance; the observed differences are ~1e-13, asserted at 1e-9).
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import mce_oracle as O
+from mcevidence_b200 import _lib
+from mcevidence_b200.synthetic import gaussian_chain
+
+pytestmark = pytest.mark.gpu
+
+LOGE_TOL = 1e-6          # north-star tolerance vs the reference
+LOGE_TIGHT = 1e-9        # what the implementation actually meets
+
+
+def oracle_knn(x, k, ref=None):
+    if ref is not None:
+        return O.knn_brute_fp64(ref, x, k)
+    d, i = O.knn_brute_fp64(x, x, k - 1, exclude_self=True)
+    return (np.concatenate((np.zeros((len(x), 1)), d), axis=1),
+            np.concatenate((np.arange(len(x))[:, None], i), axis=1))
+
+
+@pytest.mark.parametrize('n,d,k,cross', [
+    (2, 1, 2, False), (5, 2, 3, False), (129, 1, 2, False), (128, 3, 4, True), (2000, 5, 5, False),
+    (3000, 10, 5, False), (3000, 10, 9, True), (2500, 17, 4, False), (2000, 27, 5, True), (1000, 40, 3, False),
+    (1500, 64, 2, False), (4097, 6, 17, False), (20000, 8, 3, False)])
+def test_knn_bit_exact(ctx, n, d, k, cross):
+    """(DkNN, indices) contract of kneighbors (MCEvidence.py:1104): bit-exact against the FP64 oracle."""
+    rng = np.random.default_rng(1000 * d + n)
+    x = rng.normal(size=(n, d)) * (1 + rng.random(d)) + rng.normal(size=d)
+    ref = rng.normal(size=(n + 37, d)) * (1 + rng.random(d)) if cross else None
+    dk, ix, st = ctx.knn(x, k, ref=ref, identity=True)
+    od, oi = oracle_knn(x, k, ref)
+    np.testing.assert_array_equal(ix, oi)
+    np.testing.assert_array_equal(dk, od)
+    assert st['launches'] >= 4
+
+
+def test_knn_exact_rescan_path(ctx):
+    """The exhaustive FP64 kernel (used for rows the FP32 filter cannot certify) on its own."""
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=(700, 6))
+    for ref in (None, rng.normal(size=(650, 6))):
+        dk, ix, st = ctx.knn(x, 6, ref=ref, identity=True, exact_only=True)
+        od, oi = oracle_knn(x, 6, ref)
+        np.testing.assert_array_equal(ix, oi)
+        np.testing.assert_array_equal(dk, od)
+        assert st['rows_rescanned'] == 700
+
+
+def test_duplicates_and_ties(ctx):
+    """Exact ties: duplicates are neighbours at distance 0, order by index, rows re-scanned exactly."""
+    rng = np.random.default_rng(5)
+    x = np.repeat(rng.normal(size=(500, 4)), 4, axis=0)
+    dk, ix, st = ctx.knn(x, 6, identity=True)
+    od, oi = oracle_knn(x, 6)
+    np.testing.assert_array_equal(dk, od)
+    np.testing.assert_array_equal(ix, oi)
+    assert np.all(dk[:, 1:4] == 0.0) and np.all(dk[:, 4] > 0)
+    # integer lattice: massive ties at equal distances
+    g = np.stack(np.meshgrid(*[np.arange(9.0)] * 3), -1).reshape(-1, 3)
+    dk, ix, st = ctx.knn(g, 8, identity=True)
+    od, oi = oracle_knn(g, 8)
+    np.testing.assert_array_equal(ix, oi)
+    np.testing.assert_array_equal(dk, od)
+    assert st['rows_rescanned'] > 0
+
+
+def test_uncentred_far_from_origin(ctx):
+    """FP32 filter on data far from the origin (no centring with an explicit W): stays exact via verification."""
+    rng = np.random.default_rng(8)
+    x = rng.normal(size=(3000, 5)) * 1e-3 + 50.0
+    dk, ix, st = ctx.knn(x, 4, identity=True)
+    od, oi = oracle_knn(x, 4)
+    np.testing.assert_array_equal(ix, oi)
+    np.testing.assert_array_equal(dk, od)
+    assert st['rows_rescanned'] > 0        # the FP32 scores cannot separate neighbours here
+
+
+def test_query_row_ranges(ctx):
+    rng = np.random.default_rng(9)
+    x = rng.normal(size=(1000, 7))
+    od, oi = oracle_knn(x, 5)
+    for lo, hi in [(0, 1000), (0, 1), (250, 777), (999, 1000)]:
+        dk, ix, _ = ctx.knn(x, 5, identity=True, q_range=(lo, hi))
+        np.testing.assert_array_equal(ix, oi[lo:hi])
+        np.testing.assert_array_equal(dk, od[lo:hi])
+
+
+def test_strided_rows_and_ndim_prefix(ctx):
+    """First ndim columns of wider rows (MCEvidence.py:902) without a host copy."""
+    rng = np.random.default_rng(10)
+    wide = rng.normal(size=(800, 11))
+    dk, ix, _ = ctx.knn(wide, 4, ndim=6, W=np.eye(6))
+    od, oi = oracle_knn(np.ascontiguousarray(wide[:, :6]), 4)
+    np.testing.assert_array_equal(ix, oi)
+    np.testing.assert_array_equal(dk, od)
+
+
+@pytest.mark.parametrize('n,d,kmax,cross', [(4000, 5, 4, False), (6000, 10, 4, False), (6000, 10, 4, True),
+                                            (5000, 20, 8, False), (4000, 27, 4, True), (3000, 3, 2, False),
+                                            (700, 2, 1, False), (900, 12, 16, False)])
+def test_evidence_vs_oracle(ctx, n, d, kmax, cross):
+    chain, _ = gaussian_chain(n, d, seed=100 + d, nextra=2, mean_shift=1.3)
+    s, logl, w = chain[:, 2:], -chain[:, 1], chain[:, 0]
+    if cross:
+        h = n // 3
+        s1, s2, l1, w1 = s[:h], s[h:], logl[:h], w[:h]
+    else:
+        s1, s2, l1, w1 = s, None, logl, w
+    want, parts = O.evidence(s1, l1, w1, d, kmax, s2=s2, priorvolume=3.5, knn='brute', return_parts=True)
+    got = ctx.evidence(s1, l1, w1, kmax, ref=s2, ndim=d, log_sum_w=math.log(w1.sum()),
+                       log_prior_volume=math.log(3.5), want_knn=True)
+    assert got['logE'].shape == (max(2, kmax) - 1,)
+    assert np.abs(got['logE'] - want).max() < LOGE_TIGHT
+    # kneighbors-shaped arrays: identical neighbours, r_k to 1e-12 relative (Cholesky vs eig whitening)
+    np.testing.assert_array_equal(got['idx'], parts['idx'])
+    np.testing.assert_allclose(got['dknn'], parts['dknn'], rtol=1e-12, atol=0)
+    assert abs(got['log_jacobian'] - math.log(parts['cov']['J'])) < 1e-12
+    # variance: pinned by the oracle's definition only (no reference counterpart)
+    k0 = parts['k0']
+    _, ovar = O.evidence_from_dknn_log(parts['dknn'], l1, w1, d, max(2, kmax), k0, w1.sum(),
+                                       math.log(parts['cov']['J']), math.log(3.5))
+    np.testing.assert_allclose(got['var_logE'], ovar[1:], rtol=1e-9)
+
+
+def test_explicit_whitening_matrices(ctx):
+    """Reference factor eVec/sqrt(eVal) passed explicitly, and a different W for the ref set."""
+    chain, _ = gaussian_chain(3000, 6, seed=4, mean_shift=0.5)
+    s1, s2 = chain[:1400, 2:], chain[1400:, 2:]
+    l1, w1 = -chain[:1400, 1], chain[:1400, 0]
+    cs = O.covariance_stats(np.concatenate((s1, s2)))
+    W = cs['eVec'] / np.sqrt(cs['eVal'])[None, :]
+    want = O.evidence(s1, l1, w1, 6, 3, s2=s2, knn='brute')
+    got = ctx.evidence(s1, l1, w1, 3, ref=s2, W=W, mu=np.concatenate((s1, s2)).mean(0),
+                       log_jacobian=math.log(cs['J']), log_sum_w=math.log(w1.sum()))
+    assert np.abs(got['logE'] - want).max() < LOGE_TIGHT
+    cs2 = O.covariance_stats(s2)
+    W2 = cs2['eVec'] / np.sqrt(cs2['eVal'])[None, :]
+    dk, _ = O.knn_brute_fp64(s2 @ W2, s1 @ W, 4)
+    want2 = O.evidence_from_dknn_linear(dk, l1, w1, 6, 3, 0, w1.sum(), cs['J'], 0.0)[1:]
+    got2 = ctx.evidence(s1, l1, w1, 3, ref=s2, W=W, W_ref=W2, log_jacobian=math.log(cs['J']),
+                        log_sum_w=math.log(w1.sum()))
+    assert np.abs(got2['logE'] - want2).max() < LOGE_TIGHT
+
+
+def test_partials_shards_combine_to_full(ctx):
+    """Row sharding: per-shard triples combined on the host equal the one-shot result."""
+    chain, _ = gaussian_chain(5000, 8, seed=12)
+    s, l, w = chain[:, 2:], -chain[:, 1], chain[:, 0]
+    full = ctx.evidence(s, l, w, 4, log_sum_w=math.log(w.sum()))
+    parts = []
+    for lo, hi in [(0, 1700), (1700, 1701), (1701, 5000)]:
+        o = ctx.evidence(s, l, w, 4, q_range=(lo, hi), want_partials=True, log_sum_w=math.log(w.sum()))
+        parts.append(o['partials'])
+    tot = _lib.combine_partials(np.array(parts))
+    loge, var = _lib.finalize(tot, 8, False, 5000, math.log(w.sum()), full['log_jacobian'], 0.0)
+    assert np.abs(loge - full['logE']).max() < 1e-12
+    np.testing.assert_allclose(var, full['var_logE'], rtol=1e-9)
+
+
+def test_zero_distance_rows_contribute_nothing(ctx):
+    """Duplicated samples have r=0 -> volume 0 (MCEvidence.py:1110): handled as log(0) = -inf terms."""
+    chain, _ = gaussian_chain(1500, 4, seed=13)
+    chain = np.concatenate((chain, chain[:100]))
+    s, l, w = chain[:, 2:], -chain[:, 1], chain[:, 0]
+    want = O.evidence(s, l, w, 4, 3, knn='brute')
+    got = ctx.evidence(s, l, w, 3, log_sum_w=math.log(w.sum()))
+    assert np.all(np.isfinite(got['logE'])) and np.abs(got['logE'] - want).max() < LOGE_TIGHT
+
+
+def test_argument_errors(ctx):
+    x = np.random.default_rng(0).normal(size=(50, 3))
+    w = np.ones(50)
+    with pytest.raises(_lib.MCEError, match='n_neighbors <= n_samples_fit'):
+        ctx.knn(x[:4], 6, identity=True)                     # sklearn raises the same way
+    with pytest.raises(_lib.MCEError, match='neighbours'):
+        ctx.evidence(x, w, w, 40)                            # kmax beyond MCE_MAX_NEIGHBOURS
+    with pytest.raises(_lib.MCEError, match='ndim'):
+        ctx.knn(np.zeros((10, 70)), 2, identity=True)
+    with pytest.raises(_lib.MCEError, match='row range'):
+        ctx.knn(x, 2, identity=True, q_range=(10, 60))
+    degenerate = np.column_stack((x[:, 0], np.ones(50), x[:, 1]))    # a constant column: singular covariance
+    with pytest.raises(_lib.MCEError) as ei:
+        ctx.evidence(degenerate, w, w, 2)
+    assert ei.value.code == _lib.ERR_NOT_POSDEF
+    # the context survives errors
+    ctx.knn(x, 2, identity=True)
+
+
+def test_golden_reference_outputs(ctx, golden, tmp_path):
+    """End to end through the drop-in class against the frozen outputs of the unmodified reference."""
+    import MCEvidence as M
+    g = golden
+    np.random.seed(g.np_seed)
+    mce = M.MCEvidence(g.method(tmp_path), verbose=0, **g.ctor)
+    mle = mce.evidence(**g.ev)
+    assert mle.shape == g.mle.shape
+    err = np.abs(mle - g.mle).max()
+    # the ill-conditioned case is limited by the reference's own eig() accuracy, not by this path
+    assert err < (LOGE_TOL if g.name == 'auto_d6_scaled' else LOGE_TIGHT), err
+    assert mce.last_stats['launches'] >= 8
+
+
+def test_golden_knn_arrays(ctx):
+    """DkNN / indices captured inside the reference (sklearn kd-tree) vs mce_evidence(want_knn)."""
+    from conftest import Golden
+    g = Golden('auto_d8_kd')
+    c = g.chains[0]
+    out = ctx.evidence(c[:, 2:], -c[:, 1], c[:, 0], g.kmax, ndim=g.ndim, log_sum_w=math.log(c[:, 0].sum()),
+                       log_prior_volume=math.log(7.0), want_knn=True)
+    np.testing.assert_array_equal(out['idx'], g.raw['idx'])
+    np.testing.assert_allclose(out['dknn'], g.raw['dknn'], rtol=1e-12, atol=1e-300)
+    assert np.abs(out['logE'] - g.mle).max() < LOGE_TIGHT
+
+
+def test_full_size_properties_cfg2(ctx):
+    """BASELINE cfg2 (N=1e6, d=10, kmax=4, auto) at full size through size-independent properties."""
+    n, d, kmax = 1000000, 10, 4
+    chain, info = gaussian_chain(n, d, seed=0)
+    s, l, w = np.ascontiguousarray(chain[:, 2:]), -chain[:, 1], chain[:, 0]
+    out = ctx.evidence(s, l, w, kmax, log_sum_w=math.log(w.sum()), want_knn=True)
+    dk, ix = out['dknn'], out['idx']
+    assert np.all(np.diff(dk, axis=1) >= 0) and np.all(dk[:, 0] == 0) and np.all(dk[:, 1] > 0)
+    assert np.array_equal(ix[:, 0], np.arange(n)) and ix.min() >= 0 and ix.max() < n
+    assert not np.any(ix[:, 1:] == np.arange(n)[:, None])
+    # analytic evidence of the synthetic posterior (estimator bias bound)
+    assert np.abs(out['logE'] - info['lnZ']).max() < 0.1
+    # spot rows against an exhaustive FP64 numpy scan in the library's own whitened coordinates
+    cs = O.covariance_stats(s)
+    L = np.linalg.cholesky(cs['cov'])
+    y = np.linalg.solve(L, (s - s.mean(0)).T).T
+    rows = np.random.default_rng(1).choice(n, 48, replace=False)
+    for r in rows:
+        d2 = ((y - y[r]) ** 2).sum(1)
+        d2[r] = np.inf
+        nn = np.argsort(d2, kind='stable')[:kmax]
+        assert np.array_equal(ix[r, 1:], nn)
+        np.testing.assert_allclose(dk[r, 1:], np.sqrt(d2[nn]), rtol=1e-11)
+    # mutual consistency: the distance stored for (i -> j) is the distance recomputed from the rows
+    j = ix[rows, 1]
+    np.testing.assert_allclose(dk[rows, 1], np.sqrt(((y[rows] - y[j]) ** 2).sum(1)), rtol=1e-11)
+    # permutation invariance of the estimator (different tiles, chunks and summation order)
+    perm = np.random.default_rng(2).permutation(n)
+    out2 = ctx.evidence(s[perm], l[perm], w[perm], kmax, log_sum_w=math.log(w.sum()))
+    assert np.abs(out2['logE'] - out['logE']).max() < 1e-9
+    # two half-shards combine to the same answer
+    parts = [ctx.evidence(s, l, w, kmax, q_range=r, want_partials=True)['partials']
+             for r in ((0, n // 2), (n // 2, n))]
+    loge, _ = _lib.finalize(_lib.combine_partials(np.array(parts)), d, False, n, math.log(w.sum()),
+                            out['log_jacobian'], 0.0)
+    assert np.abs(loge - out['logE']).max() < 1e-11
+    assert out['stats']['rows_rescanned'] < 1000
