@@ -348,8 +348,8 @@ def main():
         achieved = 3.0 * d * pairs_launch / t_k2 / 1e12                 # algorithmic: 3d FLOP per pair (sub, mul, add)
         roofline = {'bound': 'fp32_fma', 'achieved': achieved, 'peak': fma_peak, 'unit': 'TFLOP/s',
                     'frac': achieved / fma_peak, 'traffic': None,
-                    'kernel': 'knn_filter_kernel<D=%d,TQ=%d,TR=%d,packed=%d>' % (d, stats['filter_tq'], stats['filter_tr'],
-                                                                              stats['filter_packed']),
+                    'kernel': 'knn_filter_kernel<D=%d,TQ=%d,TR=%d,packed=%d,mode=%d>' % (
+                        d, stats['filter_tq'], stats['filter_tr'], stats['filter_packed'], stats['filter_mode']),
                     'ms_per_launch': 1e3 * t_k2, 'share_of_step': float(np.sum(ms_filter)) / t_ms if world == 1 else None,
                     'peak_source': 'FMA microbenchmark in this run (mce_fma_peak): ffma %.1f, ffma2 %.1f TFLOP/s at 2 FLOP per '
                                    'lane-FMA; theoretical %.1f' % (peak['ffma'], peak['ffma2'], FP32_PEAK_THEORETICAL_TFLOPS),
@@ -369,7 +369,7 @@ def main():
                 's_per_logE': t_ms * 1e-3 / args.steps, 'logE': [float(x) for x in loge],
                 'logE_minus_analytic': [float(x - m['lnZ']) for x in loge], 'rows_rescanned_per_step': rescanned / args.steps,
                 'stage_ms': {k: stats[k] for k in ('ms_cov', 'ms_whiten', 'ms_filter', 'ms_rerank', 'ms_exact', 'ms_reduce')},
-                'filter': {k: stats[k] for k in ('filter_tq', 'filter_tr', 'filter_packed', 'ref_chunks', 'list_len',
+                'filter': {k: stats[k] for k in ('filter_tq', 'filter_tr', 'filter_packed', 'filter_mode', 'ref_chunks', 'list_len',
                                                  'filter_grid', 'filter_smem', 'filter_ctas_per_sm')}}
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline(wl, args.cpu_seconds)

@@ -99,7 +99,7 @@ typedef struct mce_stats {
     int32_t filter_smem;
     int32_t filter_ctas_per_sm;
     float   rmax;            /* largest whitened reference norm (enters the error bound) */
-    int32_t pad;
+    int32_t filter_mode;     /* 0 free-running warps, 1 CTA barrier per tile group, 2+ with register prefetch */
 } mce_stats;
 
 typedef struct mce_result {
@@ -120,7 +120,8 @@ int  mce_ctx_create(int device, mce_ctx **out);
 void mce_ctx_destroy(mce_ctx *ctx);
 /* Run on an existing CUDA stream (e.g. torch's current stream) instead of the context's own. NULL restores it. */
 int  mce_ctx_set_stream(mce_ctx *ctx, void *cuda_stream);
-/* Tuning knobs: "filter_tq", "filter_tr", "filter_packed", "ref_chunks", "list_margin", "filter_ctas". -1 = automatic. */
+/* Tuning knobs: "filter_tq", "filter_tr", "filter_packed", "filter_sync" (kernel mode 0/1/2), "ref_chunks"
+   (uniform split of the reference set), "list_margin". -1 = automatic. */
 int  mce_ctx_set_option(mce_ctx *ctx, const char *name, int value);
 
 int  mce_evidence(mce_ctx *ctx, const mce_problem *problem, mce_result *result);

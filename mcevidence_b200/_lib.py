@@ -46,11 +46,11 @@ class Stats(C.Structure):
         ('pairs', C.c_int64), ('rows_rescanned', C.c_int64),
         ('launches', C.c_int32), ('filter_tq', C.c_int32), ('filter_tr', C.c_int32), ('filter_packed', C.c_int32),
         ('ref_chunks', C.c_int32), ('list_len', C.c_int32), ('filter_grid', C.c_int32), ('filter_smem', C.c_int32),
-        ('filter_ctas_per_sm', C.c_int32), ('rmax', C.c_float), ('pad', C.c_int32),
+        ('filter_ctas_per_sm', C.c_int32), ('rmax', C.c_float), ('filter_mode', C.c_int32),
     ]
 
     def as_dict(self):
-        return {name: getattr(self, name) for name, _ in self._fields_ if name != 'pad'}
+        return {name: getattr(self, name) for name, _ in self._fields_}
 
 
 class Result(C.Structure):

@@ -88,7 +88,7 @@ struct mce_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     std::mutex mu;
-    int opt_tq = -1, opt_tr = -1, opt_packed = -1, opt_chunks = -1, opt_margin = -1, opt_ctas = -1;
+    int opt_tq = -1, opt_tr = -1, opt_packed = -1, opt_chunks = -1, opt_margin = -1, opt_ctas = -1, opt_sync = -1;
     DevBuf xq, xr, logl, w, yr, yq, tiles, cand_idx, cand_th, dknn, idx, flagged, covpart, redpart, scal, sink;
     DevScalars* hscal = nullptr;  // pinned
     cudaEvent_t ev[EV_COUNT] = {};
@@ -289,6 +289,7 @@ int run_problem(mce_ctx* c, const Run& r) {
     if (c->opt_tq > 0) cfg.tq = c->opt_tq;
     if (c->opt_tr > 0) cfg.tr = c->opt_tr;
     if (c->opt_packed >= 0) cfg.packed = c->opt_packed;
+    if (c->opt_sync >= 0) cfg.sync = c->opt_sync;
     int qpc = 0, smem = 0, ctas = 0;
     if (filter_query(d, cfg, list_len, &qpc, &smem, &ctas) != 0) {
         cudaGetLastError();
@@ -303,21 +304,36 @@ int run_problem(mce_ctx* c, const Run& r) {
     }
     const int nqblocks = (int)((nq + qpc - 1) / qpc);
     const long long nq_pad = (long long)nqblocks * qpc;
-    int chunks;
+    // Work decomposition.  Splitting the reference set multiplies the list insertions (each chunk
+    // restarts its lists), so whole-set units are used for every full wave of query blocks and
+    // only the remainder is split, to keep the last wave short.  Small problems (less than one
+    // wave of query blocks) are split throughout to fill the GPU.
+    const long long slots = (long long)c->sm_count * ctas;
+    const int max_chunks = ntiles / 4 > 1 ? (ntiles / 4 > 64 ? 64 : ntiles / 4) : 1;
+    int chunks, nfull;
     if (c->opt_chunks > 0) {
-        chunks = c->opt_chunks;
+        chunks = c->opt_chunks;      // uniform split (tuning / tests)
+        nfull = 0;
+    } else if (nqblocks >= 32 * slots) {
+        chunks = 1;
+        nfull = nqblocks;
     } else {
-        const long long slots = (long long)c->sm_count * ctas;
-        const long long target = 16 * slots;
-        chunks = (int)((target + nqblocks - 1) / nqblocks);
-        const int max_chunks = ntiles / 4 > 1 ? ntiles / 4 : 1;
-        if (chunks > max_chunks) chunks = max_chunks;
-        if (chunks > 64) chunks = 64;
-        if (chunks < 1) chunks = 1;
+        nfull = (int)((nqblocks / slots) * slots);
+        const int rem = nqblocks - nfull;
+        if (rem == 0) {
+            chunks = 1;
+        } else {
+            chunks = (int)((2 * slots + rem - 1) / rem);
+            const int cap = nfull > 0 ? 16 : 64;
+            if (chunks > cap) chunks = cap;
+            if (chunks > max_chunks) chunks = max_chunks;
+            if (chunks < 1) chunks = 1;
+        }
     }
     if (chunks > ntiles) chunks = ntiles;
     const int tiles_per_chunk = (ntiles + chunks - 1) / chunks;
     chunks = (ntiles + tiles_per_chunk - 1) / tiles_per_chunk;
+    if (chunks == 1) nfull = nqblocks;
 
     rc = c->cand_idx.ensure((size_t)chunks * list_len * nq_pad * sizeof(int));
     if (rc) return rc;
@@ -341,6 +357,7 @@ int run_problem(mce_ctx* c, const Run& r) {
         fp.tiles_per_chunk = tiles_per_chunk;
         fp.ref_chunks = chunks;
         fp.nqblocks = nqblocks;
+        fp.nfull = nfull;
         fp.list_len = list_len;
         fp.d = d;
         if (launch_filter(fp, cfg, st, &launches) != 0)
@@ -384,6 +401,7 @@ int run_problem(mce_ctx* c, const Run& r) {
     rp.self_offset = 0;
     rp.self_exclude = cross ? 0 : 1;
     rp.ref_chunks = chunks;
+    rp.nfull_queries = (int)((long long)nfull * qpc < nq ? (long long)nfull * qpc : nq);
     rp.list_len = list_len;
     rp.d = d;
     rp.k = K;
@@ -454,9 +472,10 @@ int run_problem(mce_ctx* c, const Run& r) {
     sst.filter_tq = cfg.tq;
     sst.filter_tr = cfg.tr;
     sst.filter_packed = cfg.packed;
+    sst.filter_mode = cfg.sync;
     sst.ref_chunks = chunks;
     sst.list_len = list_len;
-    sst.filter_grid = nqblocks * chunks;
+    sst.filter_grid = nfull + (nqblocks - nfull) * chunks;
     sst.filter_smem = smem;
     sst.filter_ctas_per_sm = ctas;
     memcpy(&sst.rmax, &c->hscal->rmax_bits, 4);
@@ -563,6 +582,7 @@ int mce_ctx_set_option(mce_ctx* c, const char* name, int value) {
     else if (!strcmp(name, "ref_chunks")) c->opt_chunks = value;
     else if (!strcmp(name, "list_margin")) c->opt_margin = value;
     else if (!strcmp(name, "filter_ctas")) c->opt_ctas = value;
+    else if (!strcmp(name, "filter_sync")) c->opt_sync = value;
     else return fail(MCE_ERR_ARG, "unknown option '%s'", name);
     return MCE_OK;
 }

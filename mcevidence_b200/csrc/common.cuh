@@ -56,13 +56,15 @@ struct FilterParams {
     long long self_offset;   // auto mode: reference index of query row r is r + self_offset; cross mode: any
     int self_exclude;        // 1 in auto mode
     int ntiles;
-    int tiles_per_chunk;
-    int ref_chunks;
+    int tiles_per_chunk;     // tiles per reference chunk of a split query block
+    int ref_chunks;          // chunks of a split query block
     int nqblocks;
+    int nfull;               // query blocks [0, nfull) scan the whole reference set as one unit (chunk 0);
+                             // blocks [nfull, nqblocks) are split into ref_chunks units each
     int list_len;
     int d;
 };
-struct FilterConfig { int tq, tr, packed; };
+struct FilterConfig { int tq, tr, packed, sync; };
 // Returns 0 and fills grid/smem/ctas_per_sm on success, -1 if (d, cfg) has no instantiation.
 int filter_query(int d, const FilterConfig& cfg, int list_len, int* queries_per_cta, int* smem_bytes,
                  int* ctas_per_sm);
@@ -85,6 +87,7 @@ struct RerankParams {
     long long self_offset;
     int self_exclude;
     int ref_chunks, list_len;
+    int nfull_queries;       // queries [0, nfull_queries) have one candidate chunk, the others ref_chunks
     int d, k;                // k true neighbours wanted
     int out_ld, out_col0;    // output row stride and first column (1 when a synthetic self column is kept)
     int write_self_col;      // write (0.0, own index) into column 0

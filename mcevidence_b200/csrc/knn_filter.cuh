@@ -8,6 +8,8 @@
 // registers for the whole unit.  The reference chunk is streamed as tiles of TILE_REFS rows
 // through a FILTER_STAGES-deep shared-memory ring filled by TMA bulk copies
 // (cp.async.bulk + mbarrier complete_tx; one contiguous (D+1)*TILE_REFS*4-byte block per tile).
+// Slots are handed back through per-slot "empty" mbarriers (one arrival per warp), so there is
+// no CTA-wide barrier in the main loop and warps drift freely by up to two tiles.
 //
 // Ranking score: s(q, r) = q.r - |r|^2/2 = (|q|^2 - |q - r|^2) / 2, larger is closer.  The
 // accumulator is initialised with h_r = -|r|^2/2 (an extra tile row), so one pair costs exactly
@@ -33,6 +35,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -74,29 +79,52 @@ static __device__ __noinline__ float list_insert(float* ls, int* li, int len, fl
     return fminf(s, second);
 }
 
-template <int D, int TQ, int TR, bool PACKED>
+// Ring depth: 8 tiles while they fit 48 KB, else 4.  In SYNC mode the CTA barrier is paid once
+// per group of NS/2 tiles (the group just read is refilled while the other group is consumed).
+__host__ __device__ constexpr int filter_stages(int d) { return (d + 1) * TILE_REFS * 4 * 8 <= 48 * 1024 ? 8 : FILTER_STAGES; }
+
+// MODE 0: free-running warps (per-slot empty mbarriers); 1: CTA barrier per tile group;
+// 2..4: as 1, plus row h and the first MODE-1 coordinate rows of the next step are prefetched
+// into registers half-way through the current step (hides the LDS latency at the step start)
+template <int D, int TQ, int TR, bool PACKED, int MODE>
 __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const FilterParams p) {
+    constexpr bool SYNC = MODE != 0;
+    constexpr bool PF = MODE >= 2 && PACKED;
+    constexpr int PFD = PF ? (MODE - 1 < D ? MODE - 1 : D) : 1;   // prefetched coordinate rows
     constexpr int NT = FILTER_THREADS;
     constexpr int TJ = TILE_REFS;
-    constexpr int NS = FILTER_STAGES;
+    constexpr int NS = filter_stages(D);
+    constexpr int G = NS / 2;   // tiles per barrier group (SYNC mode)
     constexpr int TILE_FLOATS = (D + 1) * TJ;
     constexpr uint32_t TILE_BYTES = TILE_FLOATS * sizeof(float);
-    static_assert(TR == 4 || TR == 8, "TR must be 4 or 8");
+    static_assert(TR == 4 || TR == 8 || TR == 16, "TR must be 4, 8 or 16");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage = reinterpret_cast<float*>(smem_raw);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * TILE_BYTES);
-    float* ls = reinterpret_cast<float*>(bars + NS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * TILE_BYTES);   // full[NS], empty[NS]
+    float* ls = reinterpret_cast<float*>(bars + 2 * NS);
     const int L = p.list_len;
     int* li = reinterpret_cast<int*>(ls + TQ * L * NT);
 
     const int tid = threadIdx.x;
-    const int qblock = blockIdx.x % p.nqblocks;
-    const int rchunk = blockIdx.x / p.nqblocks;
+    // unit -> (query block, reference chunk): the first nfull blocks are whole-set units, the
+    // remaining blocks are split so that the last wave of the grid is short
+    int qblock, rchunk, t0, t1;
+    if ((int)blockIdx.x < p.nfull) {
+        qblock = blockIdx.x;
+        rchunk = 0;
+        t0 = 0;
+        t1 = p.ntiles;
+    } else {
+        const int v = blockIdx.x - p.nfull;
+        const int rem = p.nqblocks - p.nfull;
+        rchunk = v / rem;
+        qblock = p.nfull + v % rem;
+        t0 = rchunk * p.tiles_per_chunk;
+        t1 = min(t0 + p.tiles_per_chunk, p.ntiles);
+    }
     const long long ql0 = (long long)qblock * (NT * TQ) + tid;  // local id of this thread's first query
     const long long nq = p.q_end - p.q_begin;
-    const int t0 = rchunk * p.tiles_per_chunk;
-    const int t1 = min(t0 + p.tiles_per_chunk, p.ntiles);
 
     // queries -> registers (FP64 whitened rows rounded to FP32), thresholds, empty lists
     float q[TQ][D];
@@ -118,7 +146,10 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < NS; ++s) mbar_init(smem_u32(&bars[s]), 1);
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);               // full: one arrive.expect_tx + the TMA bytes
+            mbar_init(smem_u32(&bars[NS + s]), NT / 32);    // empty: one arrive per consumer warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -127,7 +158,7 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
     const float* gt = p.tiles + (long long)t0 * TILE_FLOATS;
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < NS - 1; ++s) {
+        for (int s = 0; s < (SYNC ? G : NS - 2); ++s) {
             if (t0 + s < t1) {
                 const uint32_t bar = smem_u32(&bars[s]);
                 mbar_arrive_expect_tx(bar, TILE_BYTES);
@@ -139,13 +170,44 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
     for (int it = 0; it < t1 - t0; ++it) {
         const int slot = it % NS;
         const uint32_t parity = (it / NS) & 1;
-        if (tid == 0) {
-            const int nxt = it + NS - 1;
-            if (t0 + nxt < t1) {
-                const int ns = nxt % NS;  // the slot released by the __syncthreads of iteration it-1
-                const uint32_t bar = smem_u32(&bars[ns]);
-                mbar_arrive_expect_tx(bar, TILE_BYTES);
-                tma_bulk_g2s(smem_u32(stage + ns * TILE_FLOATS), gt + (long long)nxt * TILE_FLOATS, TILE_BYTES, bar);
+        if constexpr (SYNC) {
+            if (it % G == 0) {
+                // group boundary: every warp is done with the previous group's slots; refill them
+                // with the next group while this group (already in flight) is consumed
+                if (it > 0) __syncthreads();
+                if (tid == 0) {
+#pragma unroll
+                    for (int i = 0; i < G; ++i) {
+                        const int nxt = it + G + i;
+                        if (t0 + nxt < t1) {
+                            const int ns = nxt % NS;
+                            const uint32_t bar = smem_u32(&bars[ns]);
+                            mbar_arrive_expect_tx(bar, TILE_BYTES);
+                            tma_bulk_g2s(smem_u32(stage + ns * TILE_FLOATS), gt + (long long)nxt * TILE_FLOATS, TILE_BYTES,
+                                         bar);
+                        }
+                    }
+                }
+            }
+        }
+        if constexpr (!SYNC) {
+            if (tid == 0) {
+                // refill two tiles ahead: the slot was read during iteration it-2, so the wait on its
+                // "empty" barrier (one arrival per warp) is normally already satisfied and no warp
+                // waits for another one at a tile boundary
+                const int nxt = it + NS - 2;
+                if (t0 + nxt < t1) {
+                    const int ns = nxt % NS;
+                    if (nxt >= NS) {
+                        const uint32_t ebar = smem_u32(&bars[NS + ns]);
+                        const uint32_t eparity = ((nxt / NS) - 1) & 1;
+                        while (!mbar_try_wait(ebar, eparity)) {
+                        }
+                    }
+                    const uint32_t bar = smem_u32(&bars[ns]);
+                    mbar_arrive_expect_tx(bar, TILE_BYTES);
+                    tma_bulk_g2s(smem_u32(stage + ns * TILE_FLOATS), gt + (long long)nxt * TILE_FLOATS, TILE_BYTES, bar);
+                }
             }
         }
         {
@@ -156,6 +218,15 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
         const float* tile = stage + slot * TILE_FLOATS;
         const int jbase = (t0 + it) * TJ;
 
+        float4 pf_r[PFD][TR / 4], pf_h[TR / 4];   // PF: rows h and c < PFD of the step about to start
+        if constexpr (PF) {
+#pragma unroll
+            for (int g = 0; g < TR / 4; ++g) {
+#pragma unroll
+                for (int cc = 0; cc < PFD; ++cc) pf_r[cc][g] = *reinterpret_cast<const float4*>(tile + cc * TJ + 4 * g);
+                pf_h[g] = *reinterpret_cast<const float4*>(tile + D * TJ + 4 * g);
+            }
+        }
 #pragma unroll 1
         for (int j0 = 0; j0 < TJ; j0 += TR) {
             bool any = false;
@@ -166,15 +237,30 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
                     float2 rv[TR / 2];
 #pragma unroll
                     for (int g = 0; g < TR / 4; ++g) {
-                        const float4 r4 = *reinterpret_cast<const float4*>(tile + c * TJ + j0 + 4 * g);
+                        float4 r4;
+                        if (PF && c < PFD) r4 = pf_r[c][g];
+                        else r4 = *reinterpret_cast<const float4*>(tile + c * TJ + j0 + 4 * g);
                         rv[2 * g] = make_float2(r4.x, r4.y);
                         rv[2 * g + 1] = make_float2(r4.z, r4.w);
+                    }
+                    if (PF && c == (D / 2 >= PFD ? D / 2 : D - 1)) {
+                        // next step's first rows; past the tile end this reads (unused) bytes of the
+                        // next ring slot / barrier area, still inside the dynamic allocation
+#pragma unroll
+                        for (int g = 0; g < TR / 4; ++g) {
+#pragma unroll
+                            for (int cc = 0; cc < PFD; ++cc)
+                                pf_r[cc][g] = *reinterpret_cast<const float4*>(tile + cc * TJ + j0 + TR + 4 * g);
+                            pf_h[g] = *reinterpret_cast<const float4*>(tile + D * TJ + j0 + TR + 4 * g);
+                        }
                     }
                     if (c == 0) {
                         float2 hv[TR / 2];
 #pragma unroll
                         for (int g = 0; g < TR / 4; ++g) {
-                            const float4 h4 = *reinterpret_cast<const float4*>(tile + D * TJ + j0 + 4 * g);
+                            float4 h4;
+                            if (PF) h4 = pf_h[g];
+                            else h4 = *reinterpret_cast<const float4*>(tile + D * TJ + j0 + 4 * g);
                             hv[2 * g] = make_float2(h4.x, h4.y);
                             hv[2 * g + 1] = make_float2(h4.z, h4.w);
                         }
@@ -191,13 +277,18 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
                                 acc[t][pp] = __ffma2_rn(make_float2(q[t][c], q[t][c]), rv[pp], acc[t][pp]);
                     }
                 }
+                float best[TQ];
 #pragma unroll
-                for (int t = 0; t < TQ; ++t)
+                for (int t = 0; t < TQ; ++t) {
+                    best[t] = fmaxf(acc[t][0].x, acc[t][0].y);
 #pragma unroll
-                    for (int pp = 0; pp < TR / 2; ++pp) any |= (acc[t][pp].x > th[t]) | (acc[t][pp].y > th[t]);
+                    for (int pp = 1; pp < TR / 2; ++pp) best[t] = fmaxf(best[t], fmaxf(acc[t][pp].x, acc[t][pp].y));
+                    any |= best[t] > th[t];
+                }
                 if (any) {
 #pragma unroll
                     for (int t = 0; t < TQ; ++t) {
+                        if (!(best[t] > th[t])) continue;
 #pragma unroll
                         for (int e = 0; e < TR; ++e) {
                             const float s = (e & 1) ? acc[t][e / 2].y : acc[t][e / 2].x;
@@ -243,13 +334,18 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
                             for (int e = 0; e < TR; ++e) acc[t][e] = fmaf(q[t][c], rv[e], acc[t][e]);
                     }
                 }
+                float best[TQ];
 #pragma unroll
-                for (int t = 0; t < TQ; ++t)
+                for (int t = 0; t < TQ; ++t) {
+                    best[t] = acc[t][0];
 #pragma unroll
-                    for (int e = 0; e < TR; ++e) any |= (acc[t][e] > th[t]);
+                    for (int e = 1; e < TR; ++e) best[t] = fmaxf(best[t], acc[t][e]);
+                    any |= best[t] > th[t];
+                }
                 if (any) {
 #pragma unroll
                     for (int t = 0; t < TQ; ++t) {
+                        if (!(best[t] > th[t])) continue;
 #pragma unroll
                         for (int e = 0; e < TR; ++e) {
                             if (acc[t][e] > th[t]) {
@@ -262,7 +358,10 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
                 }
             }
         }
-        __syncthreads();  // every warp is done with this slot before thread 0 refills it
+        if constexpr (!SYNC) {
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(smem_u32(&bars[NS + slot]));   // this warp is done with the slot
+        }
     }
 
     // write the lists and final thresholds (coalesced over tid)
@@ -277,16 +376,16 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
     }
 }
 
-template <int D, int TQ, int TR, bool PACKED>
+template <int D, int TQ, int TR, bool PACKED, int MODE>
 struct FilterInst {
     static size_t smem_bytes(int list_len) {
-        return (size_t)FILTER_STAGES * (D + 1) * TILE_REFS * sizeof(float) + FILTER_STAGES * sizeof(uint64_t) +
+        return (size_t)filter_stages(D) * (D + 1) * TILE_REFS * sizeof(float) + 2 * filter_stages(D) * sizeof(uint64_t) +
                (size_t)TQ * list_len * FILTER_THREADS * (sizeof(float) + sizeof(int));
     }
     static int query(int list_len, int* qpc, int* smem, int* ctas) {
         const size_t sm = smem_bytes(list_len);
         if (sm > 227 * 1024) return -1;
-        auto kern = knn_filter_kernel<D, TQ, TR, PACKED>;
+        auto kern = knn_filter_kernel<D, TQ, TR, PACKED, MODE>;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return -1;
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, FILTER_THREADS, sm) != cudaSuccess) return -1;
@@ -297,9 +396,9 @@ struct FilterInst {
     }
     static int launch(const FilterParams& p, cudaStream_t st) {
         const size_t sm = smem_bytes(p.list_len);
-        auto kern = knn_filter_kernel<D, TQ, TR, PACKED>;
+        auto kern = knn_filter_kernel<D, TQ, TR, PACKED, MODE>;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return -1;
-        const unsigned grid = (unsigned)p.nqblocks * (unsigned)p.ref_chunks;
+        const unsigned grid = (unsigned)p.nfull + (unsigned)(p.nqblocks - p.nfull) * (unsigned)p.ref_chunks;
         kern<<<grid, FILTER_THREADS, sm, st>>>(p);
         return cudaGetLastError() == cudaSuccess ? 0 : -1;
     }
@@ -315,10 +414,10 @@ int filter_dispatch_mid(int op, int d, const FilterConfig& cfg, const FilterPara
 int filter_dispatch_hi(int op, int d, const FilterConfig& cfg, const FilterParams* p, int list_len, cudaStream_t st,
                        int* qpc, int* smem, int* ctas);   // d = 33..64
 
-#define MCE_FILTER_CASE(DD, TTQ, TTR, PK)                                                        \
-    if (d == DD && cfg.tq == TTQ && cfg.tr == TTR && cfg.packed == PK) {                         \
-        if (op == 0) return FilterInst<DD, TTQ, TTR, (PK != 0)>::query(list_len, qpc, smem, ctas); \
-        return FilterInst<DD, TTQ, TTR, (PK != 0)>::launch(*p, st);                              \
+#define MCE_FILTER_CASE1(DD, TTQ, TTR, PK, SY)                                                         \
+    if (d == DD && cfg.tq == TTQ && cfg.tr == TTR && cfg.packed == PK && cfg.sync == SY) {             \
+        if (op == 0) return FilterInst<DD, TTQ, TTR, (PK != 0), SY>::query(list_len, qpc, smem, ctas); \
+        return FilterInst<DD, TTQ, TTR, (PK != 0), SY>::launch(*p, st);                                \
     }
 
 }  // namespace mce

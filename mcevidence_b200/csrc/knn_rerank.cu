@@ -37,10 +37,12 @@ int launch_filter(const FilterParams& p, const FilterConfig& cfg, cudaStream_t s
 
 void filter_default_config(int d, int list_len, FilterConfig* cfg) {
     cfg->packed = 1;
-    // measured on B200 (profiles/r01_call01_gpu_check.log): two queries per thread with eight
-    // references per step (more resident warps) beat wider register tiles at d = 10, 20 and 27
+    // measured on B200 (profiles/r01_filter_variants.md): every tiling saturates near 55-60 TFLOP/s
+    // of executed FMA; two queries per thread x eight references per step with a CTA barrier per
+    // tile group and a one-row register prefetch is within 2 % of the best at d = 10, 20 and 27
     if (d <= 32) { cfg->tq = 2; cfg->tr = 8; }
     else { cfg->tq = 2; cfg->tr = 4; }
+    cfg->sync = 2;
     (void)list_len;
 }
 
@@ -123,7 +125,8 @@ __global__ void __launch_bounds__(128) rerank_kernel(const RerankParams p) {
     TopList top;
     top.init();
     float thmax = -CUDART_INF_F;
-    for (int r = 0; r < p.ref_chunks; ++r) {
+    const int nchunks = ql < p.nfull_queries ? 1 : p.ref_chunks;
+    for (int r = 0; r < nchunks; ++r) {
         thmax = fmaxf(thmax, p.cand_th[(long long)r * p.nq_pad + ql]);
         for (int e = 0; e < p.list_len; ++e) {
             const int id = p.cand_idx[((long long)r * p.list_len + e) * p.nq_pad + ql];
