@@ -89,7 +89,7 @@ struct mce_ctx {
     cudaStream_t stream = nullptr;
     std::mutex mu;
     int opt_tq = -1, opt_tr = -1, opt_packed = -1, opt_chunks = -1, opt_margin = -1, opt_ctas = -1, opt_sync = -1;
-    DevBuf xq, xr, logl, w, yr, yq, tiles, cand_idx, cand_th, dknn, idx, flagged, covpart, redpart, scal, sink;
+    DevBuf xq, xr, logl, w, yr, yq, tiles, cand_idx, cand_th, dknn, idx, flagged, covpart, redpart, scal, sink, exact;
     DevScalars* hscal = nullptr;  // pinned
     cudaEvent_t ev[EV_COUNT] = {};
 };
@@ -411,7 +411,10 @@ int run_problem(mce_ctx* c, const Run& r) {
     rp.flag_all = exact_only ? 1 : 0;
     launch_rerank(rp, st, &launches);
     CU(cudaEventRecord(c->ev[EV_RERANK], st));
-    launch_exact_rescan(rp, c->sm_count * 4, st, &launches);
+    const int exact_grid = c->sm_count * 4;
+    rc = c->exact.ensure(exact_scratch_bytes(exact_grid));
+    if (rc) return rc;
+    launch_exact_rescan(rp, exact_grid, c->exact.p, st, &launches);
     CU(cudaEventRecord(c->ev[EV_EXACT], st));
 
     // ---- K4: epilogue -------------------------------------------------------------------------
@@ -557,7 +560,7 @@ void mce_ctx_destroy(mce_ctx* c) {
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     DevBuf* bufs[] = {&c->xq, &c->xr, &c->logl, &c->w, &c->yr, &c->yq, &c->tiles, &c->cand_idx, &c->cand_th,
-                      &c->dknn, &c->idx, &c->flagged, &c->covpart, &c->redpart, &c->scal, &c->sink};
+                      &c->dknn, &c->idx, &c->flagged, &c->covpart, &c->redpart, &c->scal, &c->sink, &c->exact};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; ++i)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);

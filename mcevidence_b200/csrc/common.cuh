@@ -94,7 +94,8 @@ struct RerankParams {
     int flag_all;            // MCE_FLAG_EXACT_ONLY: flag every row
 };
 void launch_rerank(const RerankParams& p, cudaStream_t st, int* launches);
-void launch_exact_rescan(const RerankParams& p, int grid, cudaStream_t st, int* launches);
+size_t exact_scratch_bytes(int grid);
+void launch_exact_rescan(const RerankParams& p, int grid, void* scratch, cudaStream_t st, int* launches);
 
 // ---- K4: log-volume + logsumexp epilogue ---------------------------------------------------
 struct ReduceParams {

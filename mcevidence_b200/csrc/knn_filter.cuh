@@ -243,17 +243,6 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
                         rv[2 * g] = make_float2(r4.x, r4.y);
                         rv[2 * g + 1] = make_float2(r4.z, r4.w);
                     }
-                    if (PF && c == (D / 2 >= PFD ? D / 2 : D - 1)) {
-                        // next step's first rows; past the tile end this reads (unused) bytes of the
-                        // next ring slot / barrier area, still inside the dynamic allocation
-#pragma unroll
-                        for (int g = 0; g < TR / 4; ++g) {
-#pragma unroll
-                            for (int cc = 0; cc < PFD; ++cc)
-                                pf_r[cc][g] = *reinterpret_cast<const float4*>(tile + cc * TJ + j0 + TR + 4 * g);
-                            pf_h[g] = *reinterpret_cast<const float4*>(tile + D * TJ + j0 + TR + 4 * g);
-                        }
-                    }
                     if (c == 0) {
                         float2 hv[TR / 2];
 #pragma unroll
@@ -275,6 +264,17 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
 #pragma unroll
                             for (int pp = 0; pp < TR / 2; ++pp)
                                 acc[t][pp] = __ffma2_rn(make_float2(q[t][c], q[t][c]), rv[pp], acc[t][pp]);
+                    }
+                    if (PF && c == (D / 2 >= PFD ? D / 2 : D - 1)) {
+                        // next step's first rows; past the tile end this reads (unused) bytes of the
+                        // next ring slot / barrier area, still inside the dynamic allocation
+#pragma unroll
+                        for (int g = 0; g < TR / 4; ++g) {
+#pragma unroll
+                            for (int cc = 0; cc < PFD; ++cc)
+                                pf_r[cc][g] = *reinterpret_cast<const float4*>(tile + cc * TJ + j0 + TR + 4 * g);
+                            pf_h[g] = *reinterpret_cast<const float4*>(tile + D * TJ + j0 + TR + 4 * g);
+                        }
                     }
                 }
                 float best[TQ];

@@ -149,35 +149,49 @@ __global__ void __launch_bounds__(128) rerank_kernel(const RerankParams p) {
 }
 
 constexpr int EXACT_THREADS = 256;
+constexpr int EXACT_MAX_SEGMENTS = 64;
 
-// One CTA per flagged row: exhaustive FP64 scan, per-thread sorted lists, k rounds of block argmin.
-__global__ void __launch_bounds__(EXACT_THREADS) exact_rescan_kernel(const RerankParams p) {
+// Few flagged rows: each row is split into `seg` reference segments handled by different CTAs
+// (partial lists go to scratch and are merged by exact_merge_kernel).  Many rows: one CTA per row.
+__device__ __forceinline__ int exact_segments(int nfl, int grid) {
+    if (nfl <= 0) return 1;
+    int s = grid / nfl;
+    if (s < 1) s = 1;
+    if (s > EXACT_MAX_SEGMENTS) s = EXACT_MAX_SEGMENTS;
+    return s;
+}
+
+// Exhaustive FP64 scan of the flagged rows: per-thread sorted lists, k rounds of block argmin.
+__global__ void __launch_bounds__(EXACT_THREADS) exact_rescan_kernel(const RerankParams p, double* scratch_d,
+                                                                      long long* scratch_i) {
     __shared__ double sd[EXACT_THREADS / 32];
     __shared__ long long si[EXACT_THREADS / 32];
     __shared__ int sowner[EXACT_THREADS / 32];
     __shared__ double wd;
     __shared__ long long wi;
     __shared__ int wowner;
-    __shared__ double sq[MAX_DIM * 4];
+    __shared__ double sq[MAX_DIM];
     const int nfl = *p.nflagged;
     const int d = p.d;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int f = blockIdx.x; f < nfl; f += gridDim.x) {
+    const int nseg = exact_segments(nfl, gridDim.x);
+    const long long seg_len = (p.n_ref + nseg - 1) / nseg;
+    for (long long item = blockIdx.x; item < (long long)nfl * nseg; item += gridDim.x) {
+        const int f = (int)(item / nseg);
+        const int seg = (int)(item % nseg);
         const long long ql = p.flagged[f];
         const double* qg = p.yq + (p.q_begin + ql) * d;
         __syncthreads();
-        const double* q = qg;
-        if (d <= MAX_DIM * 4) {
-            for (int c = threadIdx.x; c < d; c += EXACT_THREADS) sq[c] = qg[c];
-            q = sq;
-        }
+        for (int c = threadIdx.x; c < d; c += EXACT_THREADS) sq[c] = qg[c];
         __syncthreads();
         const long long self = p.self_exclude ? p.q_begin + ql + p.self_offset : -1;
+        const long long j_lo = seg * seg_len;
+        const long long j_hi = min(p.n_ref, j_lo + seg_len);
         TopList top;
         top.init();
-        for (long long j = threadIdx.x; j < p.n_ref; j += EXACT_THREADS) {
+        for (long long j = j_lo + threadIdx.x; j < j_hi; j += EXACT_THREADS) {
             if (j == self) continue;
-            top.push(sq_dist_seq(q, p.yr + j * d, d), j);
+            top.push(sq_dist_seq(sq, p.yr + j * d, d), j);
         }
         TopList res;
         res.init();
@@ -209,8 +223,38 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_rescan_kernel(const Reran
             }
             __syncthreads();
         }
-        if (threadIdx.x == 0) write_row(p, ql, res);
+        if (threadIdx.x == 0) {
+            if (nseg == 1) {
+                write_row(p, ql, res);
+            } else {
+#pragma unroll
+                for (int i = 0; i < KCAP; ++i) {
+                    scratch_d[item * KCAP + i] = res.dist[i];
+                    scratch_i[item * KCAP + i] = res.idx[i];
+                }
+            }
+        }
     }
+}
+
+// Merge the per-segment lists of each flagged row (no-op when rows were not segmented).
+__global__ void __launch_bounds__(128) exact_merge_kernel(const RerankParams p, int rescan_grid, const double* scratch_d,
+                                                           const long long* scratch_i) {
+    const int nfl = *p.nflagged;
+    const int nseg = exact_segments(nfl, rescan_grid);
+    if (nseg == 1) return;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nfl) return;
+    TopList top;
+    top.init();
+    for (int seg = 0; seg < nseg; ++seg) {
+        const long long item = (long long)f * nseg + seg;
+        for (int i = 0; i < p.k; ++i) {
+            const double dd = scratch_d[item * KCAP + i];
+            if (dd < CUDART_INF) top.push(dd, scratch_i[item * KCAP + i]);
+        }
+    }
+    write_row(p, p.flagged[f], top);
 }
 
 }  // namespace
@@ -223,9 +267,15 @@ void launch_rerank(const RerankParams& p, cudaStream_t st, int* launches) {
     *launches += 1;
 }
 
-void launch_exact_rescan(const RerankParams& p, int grid, cudaStream_t st, int* launches) {
-    exact_rescan_kernel<<<grid, EXACT_THREADS, 0, st>>>(p);
-    *launches += 1;
+size_t exact_scratch_bytes(int grid) { return (size_t)grid * KCAP * (sizeof(double) + sizeof(long long)); }
+
+void launch_exact_rescan(const RerankParams& p, int grid, void* scratch, cudaStream_t st, int* launches) {
+    double* sd = reinterpret_cast<double*>(scratch);
+    long long* si = reinterpret_cast<long long*>(sd + (size_t)grid * KCAP);
+    exact_rescan_kernel<<<grid, EXACT_THREADS, 0, st>>>(p, sd, si);
+    // rows are segmented only when fewer than `grid` are flagged, so `grid` threads cover them all
+    exact_merge_kernel<<<(grid + 127) / 128, 128, 0, st>>>(p, grid, sd, si);
+    *launches += 2;
 }
 
 }  // namespace mce
