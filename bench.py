@@ -231,6 +231,8 @@ def main():
     device = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'      # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group('nccl', device_id=device)
     ctx = _lib.default_context(local_rank)
     stream = torch.cuda.current_stream(device)

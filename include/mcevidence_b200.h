@@ -118,7 +118,8 @@ int         mce_device_count(void);
 
 int  mce_ctx_create(int device, mce_ctx **out);
 void mce_ctx_destroy(mce_ctx *ctx);
-/* Run on an existing CUDA stream (e.g. torch's current stream) instead of the context's own. NULL restores it. */
+/* Run on an existing CUDA stream (e.g. torch's current stream) instead of the context's own non-blocking
+   stream; pass cudaStreamLegacy ((void*)1) for the default stream.  NULL restores the context's own stream. */
 int  mce_ctx_set_stream(mce_ctx *ctx, void *cuda_stream);
 /* Tuning knobs: "filter_tq", "filter_tr", "filter_packed", "filter_sync" (kernel mode 0/1/2), "ref_chunks"
    (uniform split of the reference set), "list_margin". -1 = automatic. */

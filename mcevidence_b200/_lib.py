@@ -144,7 +144,15 @@ class Context:
             pass
 
     def set_stream(self, cuda_stream):
-        _check(self._lib, self._lib.mce_ctx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+        """Run on an existing CUDA stream given by its raw handle (``torch.cuda.current_stream().cuda_stream``).
+        ``0`` is the legacy default stream (torch's default), passed to the library as ``cudaStreamLegacy``;
+        ``None`` restores the context's own non-blocking stream.  Work is ordered after everything already
+        queued on that stream (e.g. an NCCL broadcast of the inputs)."""
+        if cuda_stream is None:
+            handle = 0
+        else:
+            handle = int(cuda_stream) or 1          # cudaStreamLegacy == (cudaStream_t)0x1
+        _check(self._lib, self._lib.mce_ctx_set_stream(self._h, C.c_void_p(handle)))
 
     def set_option(self, name, value):
         _check(self._lib, self._lib.mce_ctx_set_option(self._h, name.encode(), int(value)))

@@ -81,7 +81,9 @@ static __device__ __noinline__ float list_insert(float* ls, int* li, int len, fl
 
 // Ring depth: 8 tiles while they fit 48 KB, else 4.  In SYNC mode the CTA barrier is paid once
 // per group of NS/2 tiles (the group just read is refilled while the other group is consumed).
-__host__ __device__ constexpr int filter_stages(int d) { return (d + 1) * TILE_REFS * 4 * 8 <= 48 * 1024 ? 8 : FILTER_STAGES; }
+__host__ __device__ constexpr int filter_stages(int d, int tq) {
+    return (tq <= 2 && (d + 1) * TILE_REFS * 4 * 8 <= 48 * 1024) ? 8 : FILTER_STAGES;   // wider register tiles keep occupancy instead
+}
 
 // MODE 0: free-running warps (per-slot empty mbarriers); 1: CTA barrier per tile group;
 // 2..4: as 1, plus row h and the first MODE-1 coordinate rows of the next step are prefetched
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
     constexpr int PFD = PF ? (MODE - 1 < D ? MODE - 1 : D) : 1;   // prefetched coordinate rows
     constexpr int NT = FILTER_THREADS;
     constexpr int TJ = TILE_REFS;
-    constexpr int NS = filter_stages(D);
+    constexpr int NS = filter_stages(D, TQ);
     constexpr int G = NS / 2;   // tiles per barrier group (SYNC mode)
     constexpr int TILE_FLOATS = (D + 1) * TJ;
     constexpr uint32_t TILE_BYTES = TILE_FLOATS * sizeof(float);
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
 template <int D, int TQ, int TR, bool PACKED, int MODE>
 struct FilterInst {
     static size_t smem_bytes(int list_len) {
-        return (size_t)filter_stages(D) * (D + 1) * TILE_REFS * sizeof(float) + 2 * filter_stages(D) * sizeof(uint64_t) +
+        return (size_t)filter_stages(D, TQ) * (D + 1) * TILE_REFS * sizeof(float) + 2 * filter_stages(D, TQ) * sizeof(uint64_t) +
                (size_t)TQ * list_len * FILTER_THREADS * (sizeof(float) + sizeof(int));
     }
     static int query(int list_len, int* qpc, int* smem, int* ctas) {

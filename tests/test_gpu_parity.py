@@ -151,19 +151,43 @@ def test_explicit_whitening_matrices(ctx):
     assert np.abs(got2['logE'] - want2).max() < LOGE_TIGHT
 
 
-def test_partials_shards_combine_to_full(ctx):
-    """Row sharding: per-shard triples combined on the host equal the one-shot result."""
-    chain, _ = gaussian_chain(5000, 8, seed=12)
-    s, l, w = chain[:, 2:], -chain[:, 1], chain[:, 0]
-    full = ctx.evidence(s, l, w, 4, log_sum_w=math.log(w.sum()))
+@pytest.mark.parametrize('cross', [False, True])
+def test_partials_shards_combine_to_full(ctx, cross):
+    """Row sharding: per-shard triples combined on the host equal the one-shot result (auto and cross)."""
+    chain, _ = gaussian_chain(9000, 8, seed=12)
+    s, l, w = chain[:5000, 2:], -chain[:5000, 1], chain[:5000, 0]
+    ref = chain[5000:, 2:] if cross else None
+    full = ctx.evidence(s, l, w, 4, ref=ref, log_sum_w=math.log(w.sum()), want_knn=True)
     parts = []
     for lo, hi in [(0, 1700), (1700, 1701), (1701, 5000)]:
-        o = ctx.evidence(s, l, w, 4, q_range=(lo, hi), want_partials=True, log_sum_w=math.log(w.sum()))
+        o = ctx.evidence(s, l, w, 4, ref=ref, q_range=(lo, hi), want_partials=True, want_knn=True,
+                         log_sum_w=math.log(w.sum()))
         parts.append(o['partials'])
+        np.testing.assert_array_equal(o['idx'], full['idx'][lo:hi])
+        np.testing.assert_array_equal(o['dknn'], full['dknn'][lo:hi])
     tot = _lib.combine_partials(np.array(parts))
-    loge, var = _lib.finalize(tot, 8, False, 5000, math.log(w.sum()), full['log_jacobian'], 0.0)
+    loge, var = _lib.finalize(tot, 8, cross, 5000, math.log(w.sum()), full['log_jacobian'], 0.0)
     assert np.abs(loge - full['logE']).max() < 1e-12
     np.testing.assert_allclose(var, full['var_logE'], rtol=1e-9)
+
+
+def test_runs_on_caller_stream(ctx):
+    """set_stream: work is ordered on the caller's stream (0 = legacy default stream), None restores."""
+    import torch
+    chain, _ = gaussian_chain(3000, 5, seed=14)
+    s, l, w = chain[:, 2:], -chain[:, 1], chain[:, 0]
+    base = ctx.evidence(s, l, w, 3, log_sum_w=0.0)['logE']
+    side = torch.cuda.Stream()
+    try:
+        for handle in (torch.cuda.current_stream().cuda_stream, side.cuda_stream):
+            ctx.set_stream(handle)
+            dev = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in (('s', s), ('l', l), ('w', w))}
+            with torch.cuda.stream(side if handle == side.cuda_stream else torch.cuda.current_stream()):
+                dev['s'].mul_(1.0)          # queued on the same stream right before the library call
+                out = ctx.evidence_device(dev['s'].data_ptr(), 3000, 5, dev['l'].data_ptr(), dev['w'].data_ptr(), 5, 3)
+            np.testing.assert_array_equal(out['logE'], base)
+    finally:
+        ctx.set_stream(None)
 
 
 def test_zero_distance_rows_contribute_nothing(ctx):
