@@ -43,6 +43,10 @@ WORKLOADS = {
     'small': (100000, 10, 4, False, 'N=1e5 d=10 kmax=4 auto'),
 }
 FP32_PEAK_THEORETICAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.4: SMs x lanes x 2 FLOP x max clock
+# dram__bytes_read.sum + dram__bytes_write.sum of one K2 launch from the ncu --set full capture of this command
+# (profiles/r01_filter_ncu_raw_default.csv: 135.9 MB read + 25.9 MB written; algorithmic: 44 MB tiles + 80 MB
+# queries + ~24 MB candidate lists -- the reference set is streamed from L2, not from HBM)
+NCU_DRAM_BYTES_PER_LAUNCH = {('cfg2', 1): 161.8e6}
 METRIC = 'knn_pair_dists_per_s'
 UNIT = 'pair-dists/s'
 
@@ -211,8 +215,12 @@ def main():
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-seconds', type=float, default=20.0)
+    ap.add_argument('--no-e2e', action='store_true', help='skip the host-API leg (long scaling runs only)')
+    ap.add_argument('--allow-short-warmup', action='store_true',
+                    help='do not raise --warmup to 3 (minutes-long steps of the cfg5 scaling run only)')
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'ours' and not args.allow_short_warmup:
+        args.warmup = max(args.warmup, 3)
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -328,20 +336,23 @@ def main():
     value = args.steps * pairs_total / (t_ms * 1e-3)
 
     # ---- e2e: public host API, pinned host arrays in, logE out --------------------------------
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        oe = step_e2e()
-    barrier()
-    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    te = float(te.item())
     h2d = (n * d + 2 * n + (n_ref * d if cross else 0)) * 8
     d2h = (kmax - 1) * 3 * 8 + 160
-    e2e_value = args.steps * pairs_total / te
+    if args.no_e2e:
+        te, e2e_value = float('nan'), None
+    else:
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        barrier()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        te = float(te.item())
+        e2e_value = args.steps * pairs_total / te
 
     if rank == 0:
         lo, hi = shard_range(n, 0, world)
@@ -349,7 +360,7 @@ def main():
         t_k2 = float(np.mean(ms_filter)) * 1e-3
         achieved = 3.0 * d * pairs_launch / t_k2 / 1e12                 # algorithmic: 3d FLOP per pair (sub, mul, add)
         roofline = {'bound': 'fp32_fma', 'achieved': achieved, 'peak': fma_peak, 'unit': 'TFLOP/s',
-                    'frac': achieved / fma_peak, 'traffic': None,
+                    'frac': achieved / fma_peak, 'traffic': NCU_DRAM_BYTES_PER_LAUNCH.get((args.workload, world)),
                     'kernel': 'knn_filter_kernel<D=%d,TQ=%d,TR=%d,packed=%d,mode=%d>' % (
                         d, stats['filter_tq'], stats['filter_tr'], stats['filter_packed'], stats['filter_mode']),
                     'ms_per_launch': 1e3 * t_k2, 'share_of_step': float(np.sum(ms_filter)) / t_ms if world == 1 else None,
@@ -366,7 +377,7 @@ def main():
                            'parallelism': 'query rows sharded over %d GPU(s), reference set replicated' % world,
                            'l2': '512 MiB memset between timed steps (not timed); working set > L2'},
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                        's_per_logE': te / args.steps},
+                        's_per_logE': None if args.no_e2e else te / args.steps},
                 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline,
                 's_per_logE': t_ms * 1e-3 / args.steps, 'logE': [float(x) for x in loge],
                 'logE_minus_analytic': [float(x - m['lnZ']) for x in loge], 'rows_rescanned_per_step': rescanned / args.steps,

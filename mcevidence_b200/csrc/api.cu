@@ -305,29 +305,32 @@ int run_problem(mce_ctx* c, const Run& r) {
     const int nqblocks = (int)((nq + qpc - 1) / qpc);
     const long long nq_pad = (long long)nqblocks * qpc;
     // Work decomposition.  Splitting the reference set multiplies the list insertions (each chunk
-    // restarts its lists), so whole-set units are used for every full wave of query blocks and
-    // only the remainder is split, to keep the last wave short.  Small problems (less than one
-    // wave of query blocks) are split throughout to fill the GPU.
+    // restarts its lists; measured ~1.2 % of a unit's time per extra chunk), so whole-set units are
+    // preferred and the split is only used to fill the last wave: blocks [0, nfull) run as whole-set
+    // units, blocks [nfull, nqblocks) are split into `chunks` units.  Both nfull = 0 (uniform split,
+    // small problems) and nfull = all full waves are scored with a wave model and the best wins.
     const long long slots = (long long)c->sm_count * ctas;
     const int max_chunks = ntiles / 4 > 1 ? (ntiles / 4 > 64 ? 64 : ntiles / 4) : 1;
-    int chunks, nfull;
+    int chunks = 1, nfull = nqblocks;
     if (c->opt_chunks > 0) {
         chunks = c->opt_chunks;      // uniform split (tuning / tests)
         nfull = 0;
-    } else if (nqblocks >= 32 * slots) {
-        chunks = 1;
-        nfull = nqblocks;
     } else {
-        nfull = (int)((nqblocks / slots) * slots);
-        const int rem = nqblocks - nfull;
-        if (rem == 0) {
-            chunks = 1;
-        } else {
-            chunks = (int)((2 * slots + rem - 1) / rem);
-            const int cap = nfull > 0 ? 16 : 64;
-            if (chunks > cap) chunks = cap;
-            if (chunks > max_chunks) chunks = max_chunks;
-            if (chunks < 1) chunks = 1;
+        double best = 1e300;
+        for (int pass = 0; pass < 2; ++pass) {
+            const long long nf = pass == 0 ? 0 : (nqblocks / slots) * slots;
+            const long long rem = nqblocks - nf;
+            if (pass == 1 && nf == 0) break;
+            for (int cc = 1; cc <= max_chunks; ++cc) {
+                if (rem == 0 && cc > 1) break;
+                const double tail_waves = (double)((rem * cc + slots - 1) / slots) / cc * (1.0 + 0.012 * (cc - 1));
+                const double t = (double)nf / slots + tail_waves;
+                if (t < best - 1e-12) {
+                    best = t;
+                    chunks = cc;
+                    nfull = (int)nf;
+                }
+            }
         }
     }
     if (chunks > ntiles) chunks = ntiles;
