@@ -141,7 +141,8 @@ int  mce_combine_partials(int nparts, int nk, const double *parts, double *out);
 int  mce_finalize(const double *partials, int nk, int d, int cross, int64_t n_query_total, double log_sum_w,
                   double log_jacobian, double log_prior_volume, double *logE, double *var_logE);
 
-/* FP32 FMA microbenchmark on the context's device: variant 0 = scalar FFMA, 1 = packed FFMA2.
+/* FP32 FMA microbenchmark on the context's device: variant 0 = scalar FFMA, 1 = packed FFMA2 (2-4: other
+   FFMA2 operand-sharing patterns, see csrc/fma_peak.cu).
    Reports achieved TFLOP/s counting 2 FLOP per lane-FMA, the roofline denominator of the filter. */
 int  mce_fma_peak(mce_ctx *ctx, int variant, int iters, double *tflops, double *ms);
 

@@ -88,7 +88,7 @@ struct mce_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     std::mutex mu;
-    int opt_tq = -1, opt_tr = -1, opt_packed = -1, opt_chunks = -1, opt_margin = -1, opt_ctas = -1, opt_sync = -1;
+    int opt_tq = -1, opt_tr = -1, opt_packed = -1, opt_chunks = -1, opt_margin = -1, opt_sync = -1;
     DevBuf xq, xr, logl, w, yr, yq, tiles, cand_idx, cand_th, dknn, idx, flagged, covpart, redpart, scal, sink, exact;
     DevScalars* hscal = nullptr;  // pinned
     cudaEvent_t ev[EV_COUNT] = {};
@@ -190,25 +190,32 @@ int run_problem(mce_ctx* c, const Run& r) {
         dlogl = p.logl;
         dw = p.weights;
     } else {
-        rc = c->xq.ensure((size_t)nq_all * d * sizeof(double));
+        // Strided rows (first d of ld columns, MCEvidence.py:902): a pitched copy from pageable memory
+        // costs ~0.2 us per row, so whole rows are copied in one flat transfer and the kernels read
+        // with the row stride; only very wide rows (ld > 16 d) are packed by a 2-D copy.
+        auto upload = [&](DevBuf& buf, const double* src, long long n, long long ld_src, const double** dptr,
+                          long long* ld_dev) -> int {
+            if (ld_src == d || ld_src <= 16LL * d) {
+                const size_t elems = (size_t)(n - 1) * ld_src + d;
+                int rc2 = buf.ensure(elems * sizeof(double));
+                if (rc2) return rc2;
+                CU(cudaMemcpyAsync(buf.p, src, elems * sizeof(double), cudaMemcpyHostToDevice, st));
+                *ld_dev = ld_src;
+            } else {
+                int rc2 = buf.ensure((size_t)n * d * sizeof(double));
+                if (rc2) return rc2;
+                CU(cudaMemcpy2DAsync(buf.p, (size_t)d * 8, src, (size_t)ld_src * 8, (size_t)d * 8, (size_t)n,
+                                     cudaMemcpyHostToDevice, st));
+                *ld_dev = d;
+            }
+            *dptr = buf.as<double>();
+            return MCE_OK;
+        };
+        rc = upload(c->xq, p.query, nq_all, p.ld_query, &dq, &ldq);
         if (rc) return rc;
-        if (p.ld_query == d)
-            CU(cudaMemcpyAsync(c->xq.p, p.query, (size_t)nq_all * d * 8, cudaMemcpyHostToDevice, st));
-        else
-            CU(cudaMemcpy2DAsync(c->xq.p, (size_t)d * 8, p.query, (size_t)p.ld_query * 8, (size_t)d * 8,
-                                 (size_t)nq_all, cudaMemcpyHostToDevice, st));
-        dq = c->xq.as<double>();
-        ldq = d;
         if (cross) {
-            rc = c->xr.ensure((size_t)n_ref * d * sizeof(double));
+            rc = upload(c->xr, p.ref, n_ref, p.ld_ref, &dr, &ldr);
             if (rc) return rc;
-            if (p.ld_ref == d)
-                CU(cudaMemcpyAsync(c->xr.p, p.ref, (size_t)n_ref * d * 8, cudaMemcpyHostToDevice, st));
-            else
-                CU(cudaMemcpy2DAsync(c->xr.p, (size_t)d * 8, p.ref, (size_t)p.ld_ref * 8, (size_t)d * 8,
-                                     (size_t)n_ref, cudaMemcpyHostToDevice, st));
-            dr = c->xr.as<double>();
-            ldr = d;
         }
         if (r.evidence) {
             rc = c->logl.ensure((size_t)nq * 8);
@@ -587,7 +594,6 @@ int mce_ctx_set_option(mce_ctx* c, const char* name, int value) {
     else if (!strcmp(name, "filter_packed")) c->opt_packed = value;
     else if (!strcmp(name, "ref_chunks")) c->opt_chunks = value;
     else if (!strcmp(name, "list_margin")) c->opt_margin = value;
-    else if (!strcmp(name, "filter_ctas")) c->opt_ctas = value;
     else if (!strcmp(name, "filter_sync")) c->opt_sync = value;
     else return fail(MCE_ERR_ARG, "unknown option '%s'", name);
     return MCE_OK;
@@ -624,9 +630,6 @@ int mce_knn(mce_ctx* c, const mce_problem* problem, int n_neighbors, double* dkn
     if (!c) return fail(MCE_ERR_ARG, "ctx is NULL");
     std::lock_guard<std::mutex> lk(c->mu);
     Run r{problem, false, n_neighbors, dknn, idx, nullptr, stats};
-    if (problem && !problem->W) {
-        // whitening estimated from the data, as in mce_evidence
-    }
     return run_problem(c, r);
 }
 
@@ -669,7 +672,7 @@ int mce_finalize(const double* partials, int nk, int d, int cross, int64_t n_que
 
 int mce_fma_peak(mce_ctx* c, int variant, int iters, double* tflops, double* ms_out) {
     if (!c || !tflops) return fail(MCE_ERR_ARG, "ctx or tflops is NULL");
-    if (variant < 0 || variant > 1 || iters < 1) return fail(MCE_ERR_ARG, "bad variant/iters");
+    if (variant < 0 || variant > 4 || iters < 1) return fail(MCE_ERR_ARG, "bad variant/iters");
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
     const int grid = c->sm_count * 8;
