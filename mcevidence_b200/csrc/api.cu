@@ -88,7 +88,7 @@ struct mce_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     std::mutex mu;
-    int opt_tq = -1, opt_tr = -1, opt_packed = -1, opt_chunks = -1, opt_margin = -1, opt_sync = -1;
+    int opt_tq = -1, opt_tr = -1, opt_packed = -1, opt_chunks = -1, opt_margin = -1, opt_sync = -1, opt_tail = -1;
     DevBuf xq, xr, logl, w, yr, yq, tiles, cand_idx, cand_th, dknn, idx, flagged, covpart, redpart, scal, sink, exact;
     DevScalars* hscal = nullptr;  // pinned
     cudaEvent_t ev[EV_COUNT] = {};
@@ -311,31 +311,36 @@ int run_problem(mce_ctx* c, const Run& r) {
     }
     const int nqblocks = (int)((nq + qpc - 1) / qpc);
     const long long nq_pad = (long long)nqblocks * qpc;
-    // Work decomposition.  Splitting the reference set multiplies the list insertions (each chunk
-    // restarts its lists; measured ~1.2 % of a unit's time per extra chunk), so whole-set units are
-    // preferred and the split is only used to fill the last wave: blocks [0, nfull) run as whole-set
-    // units, blocks [nfull, nqblocks) are split into `chunks` units.  Both nfull = 0 (uniform split,
-    // small problems) and nfull = all full waves are scored with a wave model and the best wins.
+    // Work decomposition.  Every list insertion costs about as much as ~200 pair evaluations (at d = 10;
+    // less for larger d) and every split of the reference set restarts the lists, so whole-set units are
+    // preferred: blocks [0, nfull) run as whole-set units (all full waves of query blocks), blocks
+    // [nfull, nqblocks) are split into `chunks` units to keep the last wave short; small problems
+    // (less than one wave of query blocks) are split throughout.  `chunks` minimises a simple cost
+    // model calibrated on B200 (profiles/r01_filter_variants.md):
+    //   unit(m) = m + kappa L ln(m / L)                      pair-equivalents per query of an m-reference unit
+    //   T(c)    = nfull/slots unit(n_ref) + (max(rem c / slots, 1) + 1/2) unit(n_ref / c)
     const long long slots = (long long)c->sm_count * ctas;
     const int max_chunks = ntiles / 4 > 1 ? (ntiles / 4 > 64 ? 64 : ntiles / 4) : 1;
     int chunks = 1, nfull = nqblocks;
     if (c->opt_chunks > 0) {
         chunks = c->opt_chunks;      // uniform split (tuning / tests)
         nfull = 0;
+    } else if (c->opt_tail > 0) {
+        chunks = c->opt_tail;        // whole-set units for the full waves, forced split of the remainder
+        nfull = (int)((nqblocks / slots) * slots);
     } else {
-        double best = 1e300;
-        for (int pass = 0; pass < 2; ++pass) {
-            const long long nf = pass == 0 ? 0 : (nqblocks / slots) * slots;
-            const long long rem = nqblocks - nf;
-            if (pass == 1 && nf == 0) break;
+        const double kappa = 200.0 * 11.5 / (d + 1.5);
+        auto unit = [&](double m) { return m + kappa * list_len * log(fmax(m / list_len, 2.0)); };
+        const long long nf = (nqblocks / slots) * slots;
+        const long long rem = nqblocks - nf;
+        nfull = (int)nf;
+        if (rem > 0) {
+            double best = 1e300;
             for (int cc = 1; cc <= max_chunks; ++cc) {
-                if (rem == 0 && cc > 1) break;
-                const double tail_waves = (double)((rem * cc + slots - 1) / slots) / cc * (1.0 + 0.012 * (cc - 1));
-                const double t = (double)nf / slots + tail_waves;
-                if (t < best - 1e-12) {
+                const double t = (fmax((double)rem * cc / slots, 1.0) + 0.5) * unit((double)n_ref / cc);
+                if (t < best) {
                     best = t;
                     chunks = cc;
-                    nfull = (int)nf;
                 }
             }
         }
@@ -595,6 +600,7 @@ int mce_ctx_set_option(mce_ctx* c, const char* name, int value) {
     else if (!strcmp(name, "ref_chunks")) c->opt_chunks = value;
     else if (!strcmp(name, "list_margin")) c->opt_margin = value;
     else if (!strcmp(name, "filter_sync")) c->opt_sync = value;
+    else if (!strcmp(name, "tail_chunks")) c->opt_tail = value;
     else return fail(MCE_ERR_ARG, "unknown option '%s'", name);
     return MCE_OK;
 }

@@ -4,8 +4,8 @@
 //   X      raw samples, FP64, (n, ld) row-major as handed over by the caller
 //   Y64    whitened samples, FP64, (n, d) row-major (rows are gathered by the re-rank)
 //   TILES  whitened reference set for the filter, FP32, one contiguous block per tile of
-//          TILE_REFS reference rows: (d+1) rows of TILE_REFS floats, row c < d holds
-//          coordinate c, row d holds h_j = -|y_j|^2/2.  A tile is one TMA bulk copy.
+//          TILE_REFS reference rows: (d+1) rows of TILE_REFS floats, row 0 holds
+//          h_j = -|y_j|^2/2, row c+1 holds coordinate c.  A tile is one TMA bulk copy.
 //   CAND   candidate indices int32 [ref_chunks][list_len][nq_pad] and final thresholds
 //          float [ref_chunks][nq_pad] written by the filter, read by the re-rank
 //   DKNN   FP64 (nq, K) ascending neighbour distances, IDX int64 (nq, K)

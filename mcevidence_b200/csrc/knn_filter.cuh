@@ -12,7 +12,7 @@
 // no CTA-wide barrier in the main loop and warps drift freely by up to two tiles.
 //
 // Ranking score: s(q, r) = q.r - |r|^2/2 = (|q|^2 - |q - r|^2) / 2, larger is closer.  The
-// accumulator is initialised with h_r = -|r|^2/2 (an extra tile row), so one pair costs exactly
+// accumulator is initialised with h_r = -|r|^2/2 (row 0 of the tile), so one pair costs exactly
 // D FMAs.  In the packed variant two references share one FFMA2 (fma.rn.f32x2): the query
 // coordinate is a scalar register broadcast to both halves by the instruction, the reference
 // pair comes straight out of a broadcast LDS.128.
@@ -225,8 +225,8 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
 #pragma unroll
             for (int g = 0; g < TR / 4; ++g) {
 #pragma unroll
-                for (int cc = 0; cc < PFD; ++cc) pf_r[cc][g] = *reinterpret_cast<const float4*>(tile + cc * TJ + 4 * g);
-                pf_h[g] = *reinterpret_cast<const float4*>(tile + D * TJ + 4 * g);
+                for (int cc = 0; cc < PFD; ++cc) pf_r[cc][g] = *reinterpret_cast<const float4*>(tile + (cc + 1) * TJ + 4 * g);
+                pf_h[g] = *reinterpret_cast<const float4*>(tile + 4 * g);
             }
         }
 #pragma unroll 1
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
                     for (int g = 0; g < TR / 4; ++g) {
                         float4 r4;
                         if (PF && c < PFD) r4 = pf_r[c][g];
-                        else r4 = *reinterpret_cast<const float4*>(tile + c * TJ + j0 + 4 * g);
+                        else r4 = *reinterpret_cast<const float4*>(tile + (c + 1) * TJ + j0 + 4 * g);
                         rv[2 * g] = make_float2(r4.x, r4.y);
                         rv[2 * g + 1] = make_float2(r4.z, r4.w);
                     }
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
                         for (int g = 0; g < TR / 4; ++g) {
                             float4 h4;
                             if (PF) h4 = pf_h[g];
-                            else h4 = *reinterpret_cast<const float4*>(tile + D * TJ + j0 + 4 * g);
+                            else h4 = *reinterpret_cast<const float4*>(tile + j0 + 4 * g);
                             hv[2 * g] = make_float2(h4.x, h4.y);
                             hv[2 * g + 1] = make_float2(h4.z, h4.w);
                         }
@@ -267,15 +267,16 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
                             for (int pp = 0; pp < TR / 2; ++pp)
                                 acc[t][pp] = __ffma2_rn(make_float2(q[t][c], q[t][c]), rv[pp], acc[t][pp]);
                     }
-                    if (PF && c == (D / 2 >= PFD ? D / 2 : D - 1)) {
-                        // next step's first rows; past the tile end this reads (unused) bytes of the
-                        // next ring slot / barrier area, still inside the dynamic allocation
+                    if (PF && c == (D / 2 >= PFD ? D / 2 : D - 1) && (PFD + 1 <= D || j0 + TR < TJ)) {
+                        // next step's first rows.  At the last step of a tile the addresses run into the
+                        // following rows of the same tile (h is row 0, so row PFD+1 <= D still exists);
+                        // those values are never used -- the first step is loaded at the tile start.
 #pragma unroll
                         for (int g = 0; g < TR / 4; ++g) {
 #pragma unroll
                             for (int cc = 0; cc < PFD; ++cc)
-                                pf_r[cc][g] = *reinterpret_cast<const float4*>(tile + cc * TJ + j0 + TR + 4 * g);
-                            pf_h[g] = *reinterpret_cast<const float4*>(tile + D * TJ + j0 + TR + 4 * g);
+                                pf_r[cc][g] = *reinterpret_cast<const float4*>(tile + (cc + 1) * TJ + j0 + TR + 4 * g);
+                            pf_h[g] = *reinterpret_cast<const float4*>(tile + j0 + TR + 4 * g);
                         }
                     }
                 }
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
                     float rv[TR];
 #pragma unroll
                     for (int g = 0; g < TR / 4; ++g) {
-                        const float4 r4 = *reinterpret_cast<const float4*>(tile + c * TJ + j0 + 4 * g);
+                        const float4 r4 = *reinterpret_cast<const float4*>(tile + (c + 1) * TJ + j0 + 4 * g);
                         rv[4 * g] = r4.x;
                         rv[4 * g + 1] = r4.y;
                         rv[4 * g + 2] = r4.z;
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
                         float hv[TR];
 #pragma unroll
                         for (int g = 0; g < TR / 4; ++g) {
-                            const float4 h4 = *reinterpret_cast<const float4*>(tile + D * TJ + j0 + 4 * g);
+                            const float4 h4 = *reinterpret_cast<const float4*>(tile + j0 + 4 * g);
                             hv[4 * g] = h4.x;
                             hv[4 * g + 1] = h4.y;
                             hv[4 * g + 2] = h4.z;

@@ -187,10 +187,10 @@ __global__ void __launch_bounds__(128) whiten_kernel(Segment x, int d, const dou
                 for (int a = 0; a < d; ++a) y += (xr[a] - smu[a]) * sw[a * d + c];
                 y64[row * d + c] = y;
             }
-            if (tb) tb[c * TILE_REFS + j] = (float)y;
+            if (tb) tb[(c + 1) * TILE_REFS + j] = (float)y;
             n2 += y * y;
         }
-        if (tb) tb[d * TILE_REFS + j] = valid ? (float)(-0.5 * n2) : -INFINITY;
+        if (tb) tb[j] = valid ? (float)(-0.5 * n2) : -INFINITY;   // row 0: h_j = -|y_j|^2 / 2
         if (valid) rn = __double2float_ru(sqrt(n2));
     }
     if (rmax_bits) {

@@ -20,13 +20,15 @@ ap.add_argument('--d', type=int, default=10)
 ap.add_argument('--kmax', type=int, default=4)
 ap.add_argument('--chunks', type=int, default=-1)
 ap.add_argument('--reps', type=int, default=1)
+ap.add_argument('--tail', type=int, nargs='*', default=[-1])
 ap.add_argument('--cfg', nargs='+', default=['2,8,1'])
 a = ap.parse_args()
 chain, _ = gaussian_chain(a.n, a.d, seed=0)
 s, l, w = np.ascontiguousarray(chain[:, 2:]), -chain[:, 1], chain[:, 0]
 ctx = _lib.Context(0)
 ctx.set_option('ref_chunks', a.chunks)
-for c in a.cfg:
+for c, tail in [(c, t) for c in a.cfg for t in a.tail]:
+    ctx.set_option('tail_chunks', tail)
     parts = [int(x) for x in c.split(',')]
     tq, tr, pk = parts[:3]
     sy = parts[3] if len(parts) > 3 else -1
