@@ -146,6 +146,12 @@ int  mce_finalize(const double *partials, int nk, int d, int cross, int64_t n_qu
    Reports achieved TFLOP/s counting 2 FLOP per lane-FMA, the roofline denominator of the filter. */
 int  mce_fma_peak(mce_ctx *ctx, int variant, int iters, double *tflops, double *ms);
 
+/* Host-side chain ingestion (next-row N1): parse a whitespace-separated text chain (`#` comments, blank
+   lines skipped) with `nthreads` threads (<= 0: all cores) into a malloc'ed row-major (nrows, ncols) array --
+   the np.loadtxt call of MCEvidence.py:564, same correctly-rounded values.  Free with mce_free_host. */
+int  mce_read_chain_text(const char *path, int nthreads, double **data, int64_t *nrows, int64_t *ncols);
+void mce_free_host(void *p);
+
 #ifdef __cplusplus
 }
 #endif

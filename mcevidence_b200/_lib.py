@@ -96,6 +96,9 @@ def load_library():
         lib.mce_finalize.argtypes = [c_double_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_double,
                                      C.c_double, c_double_p, c_double_p]
         lib.mce_fma_peak.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p]
+        lib.mce_read_chain_text.argtypes = [C.c_char_p, C.c_int, C.POINTER(c_double_p), c_int64_p, c_int64_p]
+        lib.mce_free_host.argtypes = [C.c_void_p]
+        lib.mce_free_host.restype = None
         _lib = lib
         return lib
 
@@ -224,6 +227,30 @@ class Context:
         out.update({'logE': loge, 'var_logE': var, 'log_jacobian': r.log_jacobian, 'stats': r.stats.as_dict()})
         return out
 
+    def evidence_batch(self, problems):
+        """``mce_evidence_batch``: a list of dicts with the keyword arguments of :meth:`evidence`
+        (``query, logl, weights, kmax`` and optionally ``ref, ndim, log_sum_w, log_prior_volume``), run back
+        to back on this context (chain-per-GPU batching).  Returns a list of result dicts."""
+        n = len(problems)
+        keep, outs = [], []
+        parr = (Problem * n)()
+        rarr = (Result * n)()
+        for i, kw in enumerate(problems):
+            kw = dict(kw)
+            p, _ = self._problem(kw['query'], kw.get('ref'), kw['logl'], kw['weights'], kw.get('ndim'), kw['kmax'],
+                                 kw.get('W'), kw.get('W_ref'), kw.get('mu'), kw.get('log_jacobian', 0.0),
+                                 kw.get('log_sum_w', 0.0), kw.get('log_prior_volume', 0.0), None, 0, keep)
+            parr[i] = p
+            kk = max(2, int(kw['kmax']))
+            loge, var = np.empty(kk - 1), np.empty(kk - 1)
+            rarr[i].logE, rarr[i].var_logE = _ptr(loge), _ptr(var)
+            outs.append({'logE': loge, 'var_logE': var})
+        _check(self._lib, self._lib.mce_evidence_batch(self._h, n, parr, rarr))
+        for i, o in enumerate(outs):
+            o['log_jacobian'] = rarr[i].log_jacobian
+            o['stats'] = rarr[i].stats.as_dict()
+        return outs
+
     def knn(self, query, n_neighbors, ref=None, ndim=None, W=None, W_ref=None, mu=None, q_range=None,
             exact_only=False, identity=False):
         """``mce_knn``: ``(dknn, idx, stats)`` with sklearn's ``kneighbors`` contract.
@@ -305,6 +332,21 @@ def finalize(partials, ndim, cross, n_query_total, log_sum_w, log_jacobian, log_
                                  float(log_prior_volume), loge.ctypes.data_as(c_double_p),
                                  var.ctypes.data_as(c_double_p)))
     return loge, var
+
+
+def read_chain_text(path, nthreads=0):
+    """``mce_read_chain_text``: multi-threaded parse of a text chain into a float64 (rows, columns) array."""
+    lib = load_library()
+    data = c_double_p()
+    nrows, ncols = C.c_int64(), C.c_int64()
+    rc = lib.mce_read_chain_text(os.fsencode(path), int(nthreads), C.byref(data), C.byref(nrows), C.byref(ncols))
+    if rc != 0:
+        raise MCEError(rc, 'cannot parse %s as a rectangular whitespace-separated table' % path)
+    try:
+        arr = np.ctypeslib.as_array(data, shape=(nrows.value, ncols.value)).copy()
+    finally:
+        lib.mce_free_host(data)
+    return arr
 
 
 _default_ctx = {}

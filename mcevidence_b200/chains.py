@@ -45,11 +45,16 @@ class data_set(object):
 def read_chain_file(fname):
     """Parse a whitespace-separated chain file into a C-contiguous float64 ``(rows, columns)`` array.
 
-    Values are those of ``np.loadtxt`` (correctly rounded decimal->double, ``#`` comments), which the
-    reference uses (``MCEvidence.py:564``); numpy >= 1.23 parses in C (~130 MB/s), which beats pandas'
-    round-trip parser by 6x on chain files, so it is used directly.
+    Same values as the reference's ``np.loadtxt`` (``MCEvidence.py:564``: correctly rounded
+    decimal->double, ``#`` comments, blank lines skipped), parsed by the multi-threaded reader of the
+    shared library (``mce_read_chain_text``); anything it does not accept (ragged rows, exotic number
+    formats) is handed to ``np.loadtxt`` so that error behaviour stays numpy's.
     """
-    return np.ascontiguousarray(np.atleast_2d(np.loadtxt(fname)), dtype=np.float64)
+    try:
+        from . import _lib
+        return _lib.read_chain_text(fname)
+    except Exception:
+        return np.ascontiguousarray(np.atleast_2d(np.loadtxt(fname)), dtype=np.float64)
 
 
 class SamplesMIXIN(object):

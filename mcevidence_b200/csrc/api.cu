@@ -182,7 +182,7 @@ int run_problem(mce_ctx* c, const Run& r) {
     CU(cudaEventRecord(c->ev[EV_START], st));
 
     // ---- inputs on the device ------------------------------------------------------------
-    const double *dq, *dr = nullptr, *dlogl = nullptr, *dw = nullptr;
+    const double *dq = nullptr, *dr = nullptr, *dlogl = nullptr, *dw = nullptr;
     long long ldq = p.ld_query, ldr = p.ld_ref;
     if (devptr) {
         dq = p.query;

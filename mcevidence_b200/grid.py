@@ -46,13 +46,14 @@ def evidence_many(chains, kmax=2, ndim=None, priorvolume=1.0, device=0, ctx=None
         rank, world = dist.get_rank(group), dist.get_world_size(group)
     mine = assign_largest_first([len(c) for c in chains], world)[rank]
     ctx = ctx or _lib.default_context(device)
-    local = {}
+    probs = []
     for i in mine:
         c = np.asarray(chains[i], dtype=np.float64)
         nd = c.shape[1] - 2 if ndims[i] is None else int(ndims[i])
-        out = ctx.evidence(c[:, 2:], -c[:, 1], c[:, 0], kmax, ndim=nd, log_sum_w=math.log(np.sum(c[:, 0])),
-                           log_prior_volume=math.log(pvs[i]))
-        local[i] = (out['logE'], out['var_logE'], out['stats']['ms_total'])
+        probs.append({'query': c[:, 2:], 'logl': -c[:, 1], 'weights': c[:, 0], 'kmax': kmax, 'ndim': nd,
+                      'log_sum_w': math.log(np.sum(c[:, 0])), 'log_prior_volume': math.log(pvs[i])})
+    outs = ctx.evidence_batch(probs) if probs else []          # one C call: mce_evidence_batch
+    local = {i: (o['logE'], o['var_logE'], o['stats']['ms_total']) for i, o in zip(mine, outs)}
     if world > 1:
         gathered = [None] * world
         dist.all_gather_object(gathered, local, group=group)

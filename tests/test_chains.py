@@ -146,3 +146,31 @@ def test_importance_sample_and_burn_partition():
     ms.removeBurn(0.25, name='s1')
     assert ms.get_shape()[0] == 30
     assert ms.removeBurn(7) == 7
+
+
+def test_native_chain_reader_matches_loadtxt(tmp_path):
+    """mce_read_chain_text (multi-threaded strtod) returns exactly what np.loadtxt returns."""
+    from mcevidence_b200 import _lib
+    rng = np.random.default_rng(6)
+    x = rng.normal(size=(20000, 9)) * 10.0 ** rng.integers(-20, 20, size=(20000, 9))
+    f = str(tmp_path / 'wide.txt')
+    np.savetxt(f, x, fmt='%.17g')
+    for nt in (1, 3, 0):
+        np.testing.assert_array_equal(_lib.read_chain_text(f, nt), x)
+    g = str(tmp_path / 'messy.txt')
+    with open(g, 'w') as fh:
+        fh.write('# weight loglike p1\n1 2.5 3e-3\n\n  4 5 6   # trailing comment\n7\t8\t-9.0E+1\r\n   \n10 11 12')
+    want = np.loadtxt(g)
+    np.testing.assert_array_equal(read_chain_file(g), want)
+    assert read_chain_file(g).flags.c_contiguous and read_chain_file(g).shape == (4, 3)
+    r = str(tmp_path / 'ragged.txt')
+    with open(r, 'w') as fh:
+        fh.write('1 2 3\n4 5\n')
+    with pytest.raises(_lib.MCEError):
+        _lib.read_chain_text(r)
+    with pytest.raises(ValueError):          # numpy's own error for what the fast path rejects
+        read_chain_file(r)
+    one = str(tmp_path / 'one.txt')
+    with open(one, 'w') as fh:
+        fh.write('1 2 3 4\n')
+    assert read_chain_file(one).shape == (1, 4)

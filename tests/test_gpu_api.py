@@ -90,3 +90,12 @@ def test_grid_of_chains_batched():
     for c, le in zip(chains, loge):
         want = O.evidence(c[:, 2:], -c[:, 1], c[:, 0], c.shape[1] - 2, 2, knn='brute')
         assert np.abs(le - want).max() < 1e-9
+    # per-chain ndim / prior volume, and an error inside a batch names the failing problem
+    loge2, _, _ = evidence_many(chains[:2], kmax=3, ndim=[4, 5], priorvolume=[2.0, 3.0])
+    for c, nd, pv, le in zip(chains[:2], (4, 5), (2.0, 3.0), loge2):
+        want = O.evidence(c[:, 2:], -c[:, 1], c[:, 0], nd, 3, priorvolume=pv, knn='brute')
+        assert np.abs(le - want).max() < 1e-9
+    from mcevidence_b200 import _lib
+    bad = np.column_stack((np.ones(50), np.zeros(50), np.ones((50, 2))))      # constant columns: singular covariance
+    with pytest.raises(_lib.MCEError, match='problem 1'):
+        evidence_many([chains[0], bad], kmax=2)
