@@ -45,19 +45,23 @@ extern "C" {
 #define MCE_FLAG_DEVICE_PTRS  1  /* query/ref/logl/weights and result arrays are device pointers on the context's device */
 #define MCE_FLAG_PARTIALS     2  /* also return the per-k (max, sum, sum2) partials (result.partials) */
 #define MCE_FLAG_EXACT_ONLY   4  /* skip the FP32 filter: exhaustive FP64 search for every row (validation) */
+#define MCE_FLAG_F32_SAMPLES  8  /* query and ref point to float32 arrays (strides in elements); every other array
+                                    stays float64.  The values are widened on load: results equal those of the same
+                                    call on the widened float64 copy, bit for bit */
 
 typedef struct mce_ctx mce_ctx;
 
 /* One evidence problem = one batch of MCEvidence.evidence() (MCEvidence.py:1041-1131). */
 typedef struct mce_problem {
-    const double *query;     /* s1 samples, (n_query, ld_query) row-major, first d columns used (MCEvidence.py:902) */
-    const double *ref;       /* s2 samples for cross mode (MCEvidence.py:1075-1094), or NULL: auto mode,
+    const void   *query;     /* s1 samples, float64 (or float32 with MCE_FLAG_F32_SAMPLES), (n_query, ld_query) row-major,
+                                first d columns used (MCEvidence.py:902) */
+    const void   *ref;       /* s2 samples for cross mode (MCEvidence.py:1075-1094), or NULL: auto mode,
                                 neighbours searched in the query set itself with each row excluded (k0=1, :1099) */
     const double *logl;      /* n_query log-likelihoods: -loglikes, negated again for pos_lnp (MCEvidence.py:399,1060) */
     const double *weights;   /* n_query sample weights (MCEvidence.py:400,1117) */
     int64_t n_query;
     int64_t n_ref;           /* ignored when ref == NULL */
-    int64_t ld_query;        /* row stride of query in doubles (>= d) */
+    int64_t ld_query;        /* row stride of query in elements (>= d) */
     int64_t ld_ref;
     int64_t q_begin;         /* only rows [q_begin, q_end) of query are searched and reduced (row sharding over */
     int64_t q_end;           /* GPUs); covariance and, in auto mode, the reference set still use all rows. 0,0 = all */

@@ -17,6 +17,7 @@ MCE_MAX_NEIGHBOURS = 16
 FLAG_DEVICE_PTRS = 1
 FLAG_PARTIALS = 2
 FLAG_EXACT_ONLY = 4
+FLAG_F32_SAMPLES = 8
 
 ERR_NOT_POSDEF = -3
 
@@ -112,13 +113,14 @@ def _ptr(a):
     return None if a is None else a.ctypes.data
 
 
-def _f64(a, name):
-    """float64 array whose rows are contiguous (strided rows are passed through ``ld``)."""
+def _f64(a, name, allow_f32=False):
+    """float64 (or, for sample arrays, float32) array whose rows are contiguous (strided rows go through ``ld``)."""
     a = np.asarray(a)
-    if a.dtype != np.float64:
+    if a.dtype != np.float64 and not (allow_f32 and a.dtype == np.float32):
         a = a.astype(np.float64)
     if a.ndim == 2:
-        if a.strides[1] != 8 or a.strides[0] % 8 or a.strides[0] < 8 * a.shape[1]:
+        isz = a.dtype.itemsize
+        if a.strides[1] != isz or a.strides[0] % isz or a.strides[0] < isz * a.shape[1]:
             a = np.ascontiguousarray(a)
     elif not a.flags.c_contiguous:
         a = np.ascontiguousarray(a)
@@ -164,7 +166,12 @@ class Context:
     def _problem(self, query, ref, logl, weights, ndim, kmax, W, W_ref, mu, log_jacobian, log_sum_w,
                  log_prior_volume, q_range, flags, keep):
         p = Problem()
-        query = _f64(query, 'query')
+        # float32 sample arrays are passed as they are (MCE_FLAG_F32_SAMPLES) when query and ref agree
+        f32 = np.asarray(query).dtype == np.float32 and (ref is None or np.asarray(ref).dtype == np.float32)
+        query = _f64(query, 'query', allow_f32=f32)
+        isz = query.dtype.itemsize
+        if f32:
+            flags |= FLAG_F32_SAMPLES
         keep.append(query)
         if query.ndim != 2:
             raise ValueError('query must be 2-D')
@@ -172,14 +179,14 @@ class Context:
         if ndim > query.shape[1]:
             raise ValueError('ndim=%d exceeds the %d sample columns' % (ndim, query.shape[1]))
         p.query = _ptr(query)
-        p.n_query, p.ld_query = query.shape[0], query.strides[0] // 8
+        p.n_query, p.ld_query = query.shape[0], query.strides[0] // isz
         if ref is not None:
-            ref = _f64(ref, 'ref')
+            ref = _f64(ref, 'ref', allow_f32=f32)
             keep.append(ref)
             if ref.ndim != 2 or ref.shape[1] < ndim:
                 raise ValueError('ref must be 2-D with at least ndim columns')
             p.ref = _ptr(ref)
-            p.n_ref, p.ld_ref = ref.shape[0], ref.strides[0] // 8
+            p.n_ref, p.ld_ref = ref.shape[0], ref.strides[0] // isz
         for name, arr in (('logl', logl), ('weights', weights)):
             if arr is not None:
                 arr = _f64(arr, name).reshape(-1)

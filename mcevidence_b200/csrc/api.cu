@@ -136,6 +136,8 @@ int run_problem(mce_ctx* c, const Run& r) {
     CU(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     const bool devptr = (p.flags & MCE_FLAG_DEVICE_PTRS) != 0;
+    const int f32 = (p.flags & MCE_FLAG_F32_SAMPLES) ? 1 : 0;   // query / ref are float32 arrays
+    const size_t esz = f32 ? sizeof(float) : sizeof(double);
     const bool cross = p.ref != nullptr;
     const int d = p.d;
     const long long nq_all = p.n_query;
@@ -182,7 +184,8 @@ int run_problem(mce_ctx* c, const Run& r) {
     CU(cudaEventRecord(c->ev[EV_START], st));
 
     // ---- inputs on the device ------------------------------------------------------------
-    const double *dq = nullptr, *dr = nullptr, *dlogl = nullptr, *dw = nullptr;
+    const void *dq = nullptr, *dr = nullptr;
+    const double *dlogl = nullptr, *dw = nullptr;
     long long ldq = p.ld_query, ldr = p.ld_ref;
     if (devptr) {
         dq = p.query;
@@ -193,22 +196,22 @@ int run_problem(mce_ctx* c, const Run& r) {
         // Strided rows (first d of ld columns, MCEvidence.py:902): a pitched copy from pageable memory
         // costs ~0.2 us per row, so whole rows are copied in one flat transfer and the kernels read
         // with the row stride; only very wide rows (ld > 16 d) are packed by a 2-D copy.
-        auto upload = [&](DevBuf& buf, const double* src, long long n, long long ld_src, const double** dptr,
+        auto upload = [&](DevBuf& buf, const void* src, long long n, long long ld_src, const void** dptr,
                           long long* ld_dev) -> int {
             if (ld_src == d || ld_src <= 16LL * d) {
                 const size_t elems = (size_t)(n - 1) * ld_src + d;
-                int rc2 = buf.ensure(elems * sizeof(double));
+                int rc2 = buf.ensure(elems * esz);
                 if (rc2) return rc2;
-                CU(cudaMemcpyAsync(buf.p, src, elems * sizeof(double), cudaMemcpyHostToDevice, st));
+                CU(cudaMemcpyAsync(buf.p, src, elems * esz, cudaMemcpyHostToDevice, st));
                 *ld_dev = ld_src;
             } else {
-                int rc2 = buf.ensure((size_t)n * d * sizeof(double));
+                int rc2 = buf.ensure((size_t)n * d * esz);
                 if (rc2) return rc2;
-                CU(cudaMemcpy2DAsync(buf.p, (size_t)d * 8, src, (size_t)ld_src * 8, (size_t)d * 8, (size_t)n,
+                CU(cudaMemcpy2DAsync(buf.p, (size_t)d * esz, src, (size_t)ld_src * esz, (size_t)d * esz, (size_t)n,
                                      cudaMemcpyHostToDevice, st));
                 *ld_dev = d;
             }
-            *dptr = buf.as<double>();
+            *dptr = buf.p;
             return MCE_OK;
         };
         rc = upload(c->xq, p.query, nq_all, p.ld_query, &dq, &ldq);
@@ -242,8 +245,8 @@ int run_problem(mce_ctx* c, const Run& r) {
         rc = c->covpart.ensure((size_t)grid * (npairs > d ? npairs : d) * 8);
         if (rc) return rc;
         CovWorkspace ws{c->covpart.as<double>(), ds->mean, ds->W, &ds->logj, &ds->status};
-        Segment a{dq, nq_all, ldq};
-        Segment b{cross ? dr : nullptr, cross ? n_ref : 0, ldr};
+        Segment a{dq, nq_all, ldq, f32};
+        Segment b{cross ? dr : nullptr, cross ? n_ref : 0, ldr, f32};
         launch_covariance(a, b, d, ws, grid, st, &launches);
         dW = ds->W;
         dWr = ds->W;
@@ -274,14 +277,14 @@ int run_problem(mce_ctx* c, const Run& r) {
     if (rc) return rc;
     const double* yq_base;
     if (cross) {
-        launch_whiten(Segment{dr, n_ref, ldr}, d, dWr, dmu, c->yr.as<double>(), c->tiles.as<float>(), &ds->rmax_bits, st,
+        launch_whiten(Segment{dr, n_ref, ldr, f32}, d, dWr, dmu, c->yr.as<double>(), c->tiles.as<float>(), &ds->rmax_bits, st,
                       &launches);
         rc = c->yq.ensure((size_t)nq * d * 8);
         if (rc) return rc;
-        launch_whiten(Segment{dq + qb * ldq, nq, ldq}, d, dW, dmu, c->yq.as<double>(), nullptr, nullptr, st, &launches);
+        launch_whiten(Segment{dq, nq_all, ldq, f32}.rows_from(qb, nq), d, dW, dmu, c->yq.as<double>(), nullptr, nullptr, st, &launches);
         yq_base = c->yq.as<double>() - qb * d;
     } else {
-        launch_whiten(Segment{dq, nq_all, ldq}, d, dW, dmu, c->yr.as<double>(), c->tiles.as<float>(), &ds->rmax_bits, st,
+        launch_whiten(Segment{dq, nq_all, ldq, f32}, d, dW, dmu, c->yr.as<double>(), c->tiles.as<float>(), &ds->rmax_bits, st,
                       &launches);
         yq_base = c->yr.as<double>();
     }

@@ -21,10 +21,21 @@ constexpr int FILTER_STAGES = 4;      // TMA ring depth
 constexpr int KCAP = 16;              // == MCE_MAX_NEIGHBOURS
 constexpr int MAX_DIM = 64;           // == MCE_MAX_DIM
 
-struct Segment {            // one strided FP64 sample array
-    const double* x;
+struct Segment {            // one strided sample array, float64 or float32 (MCE_FLAG_F32_SAMPLES)
+    const void* x;
     long long n;
-    long long ld;
+    long long ld;           // row stride in elements
+    int f32;
+    __host__ __device__ __forceinline__ double at(long long r, int c) const {
+        return f32 ? (double)static_cast<const float*>(x)[r * ld + c] : static_cast<const double*>(x)[r * ld + c];
+    }
+    __host__ __device__ __forceinline__ Segment rows_from(long long r0, long long count) const {
+        Segment s = *this;
+        s.x = f32 ? static_cast<const void*>(static_cast<const float*>(x) + r0 * ld)
+                  : static_cast<const void*>(static_cast<const double*>(x) + r0 * ld);
+        s.n = count;
+        return s;
+    }
 };
 
 // ---- K0: covariance, Cholesky, whitening matrix -------------------------------------------

@@ -17,8 +17,8 @@ namespace {
 constexpr int COV_THREADS = 256;
 constexpr int COV_PAIRS_PER_THREAD = (MAX_DIM * (MAX_DIM + 1) / 2 + COV_THREADS - 1) / COV_THREADS;  // 9
 
-__device__ __forceinline__ const double* seg_row(const Segment& a, const Segment& b, long long r) {
-    return r < a.n ? a.x + r * a.ld : b.x + (r - a.n) * b.ld;
+__device__ __forceinline__ double seg_at(const Segment& a, const Segment& b, long long r, int c) {
+    return r < a.n ? a.at(r, c) : b.at(r - a.n, c);
 }
 
 // Rows per staged chunk so that the chunk fits 32 KB of shared memory.
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(COV_THREADS) colsum_kernel(Segment a, Segment 
         const int nr = (int)min((long long)rc, n - r0);
         for (int e = threadIdx.x; e < nr * d; e += COV_THREADS) {
             const int r = e / d, c = e - r * d;
-            xs[e] = seg_row(a, b, r0 + r)[c];
+            xs[e] = seg_at(a, b, r0 + r, c);
         }
         __syncthreads();
         if (threadIdx.x < d)
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(COV_THREADS) scatter_kernel(Segment a, Segment
         const int nr = (int)min((long long)rc, n - r0);
         for (int e = threadIdx.x; e < nr * d; e += COV_THREADS) {
             const int r = e / d, c = e - r * d;
-            xs[e] = seg_row(a, b, r0 + r)[c] - smean[c];
+            xs[e] = seg_at(a, b, r0 + r, c) - smean[c];
         }
         __syncthreads();
 #pragma unroll
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(128) whiten_kernel(Segment x, int d, const dou
     float rn = 0.f;
     if (row < nrows_padded) {
         const bool valid = row < x.n;
-        const double* xr = x.x + (valid ? row : 0) * x.ld;
+        const long long xrow = valid ? row : 0;
         float* tb = nullptr;
         int j = 0;
         if (tiles) {
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(128) whiten_kernel(Segment x, int d, const dou
         for (int c = 0; c < d; ++c) {
             double y = 0.0;
             if (valid) {
-                for (int a = 0; a < d; ++a) y += (xr[a] - smu[a]) * sw[a * d + c];
+                for (int a = 0; a < d; ++a) y += (x.at(xrow, a) - smu[a]) * sw[a * d + c];
                 y64[row * d + c] = y;
             }
             if (tb) tb[(c + 1) * TILE_REFS + j] = (float)y;

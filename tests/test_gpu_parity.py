@@ -190,6 +190,27 @@ def test_runs_on_caller_stream(ctx):
         ctx.set_stream(None)
 
 
+def test_float32_sample_arrays(ctx):
+    """float32 samples through the ABI (MCE_FLAG_F32_SAMPLES): widened on load, so the results equal those of
+    the widened float64 copy bit for bit -- auto and cross, contiguous and strided."""
+    chain, _ = gaussian_chain(5000, 6, seed=15, nextra=2)
+    x32 = chain[:, 2:].astype(np.float32)
+    l, w = -chain[:, 1], chain[:, 0]
+    for ref32 in (None, x32[3000:]):
+        q32 = x32 if ref32 is None else x32[:3000]
+        lq, wq = (l, w) if ref32 is None else (l[:3000], w[:3000])
+        a = ctx.evidence(q32, lq, wq, 4, ref=ref32, ndim=6, log_sum_w=0.0, want_knn=True)
+        b = ctx.evidence(q32.astype(np.float64), lq, wq, 4, ref=None if ref32 is None else ref32.astype(np.float64),
+                         ndim=6, log_sum_w=0.0, want_knn=True)
+        np.testing.assert_array_equal(a['logE'], b['logE'])
+        np.testing.assert_array_equal(a['idx'], b['idx'])
+        np.testing.assert_array_equal(a['dknn'], b['dknn'])
+    dk, ix, _ = ctx.knn(np.ascontiguousarray(x32[:, :6]), 4, identity=True)
+    od, oi = oracle_knn(x32[:, :6].astype(np.float64), 4)
+    np.testing.assert_array_equal(ix, oi)
+    np.testing.assert_array_equal(dk, od)
+
+
 def test_zero_distance_rows_contribute_nothing(ctx):
     """Duplicated samples have r=0 -> volume 0 (MCEvidence.py:1110): handled as log(0) = -inf terms."""
     chain, _ = gaussian_chain(1500, 4, seed=13)
