@@ -270,10 +270,11 @@ int run_problem(mce_ctx* c, const Run& r) {
     CU(cudaEventRecord(c->ev[EV_COV], st));
 
     // ---- K1: whitening on load ------------------------------------------------------------
-    const int ntiles = (int)((n_ref + TILE_REFS - 1) / TILE_REFS);
+    const int TJ = tile_refs(d);
+    const int ntiles = (int)((n_ref + TJ - 1) / TJ);
     rc = c->yr.ensure((size_t)n_ref * d * 8);
     if (rc) return rc;
-    rc = c->tiles.ensure((size_t)ntiles * (d + 1) * TILE_REFS * sizeof(float));
+    rc = c->tiles.ensure((size_t)ntiles * (d + 1) * TJ * sizeof(float));
     if (rc) return rc;
     const double* yq_base;
     if (cross) {
@@ -301,6 +302,15 @@ int run_problem(mce_ctx* c, const Run& r) {
     if (c->opt_packed >= 0) cfg.packed = c->opt_packed;
     if (c->opt_sync >= 0) cfg.sync = c->opt_sync;
     int qpc = 0, smem = 0, ctas = 0;
+    if (c->opt_tq <= 0 && c->opt_tr <= 0 && c->opt_packed < 0 && c->opt_sync < 0 && d <= 16) {
+        // Low ndim, large problems: four queries per thread (half the shared-memory traffic per FMA, two-row
+        // prefetch) is 2-8 % faster once its 512-query blocks fill at least one wave; below that the
+        // 256-query blocks of the default fill the GPU with fewer reference splits.
+        FilterConfig wide{4, 8, 1, 3};
+        int q4 = 0, s4 = 0, c4 = 0;
+        if (filter_query(d, wide, list_len, &q4, &s4, &c4) == 0 && nq / q4 >= (long long)c->sm_count * c4) cfg = wide;
+        else cudaGetLastError();
+    }
     if (filter_query(d, cfg, list_len, &qpc, &smem, &ctas) != 0) {
         cudaGetLastError();
         FilterConfig def;

@@ -4,7 +4,7 @@
 //   X      raw samples, FP64, (n, ld) row-major as handed over by the caller
 //   Y64    whitened samples, FP64, (n, d) row-major (rows are gathered by the re-rank)
 //   TILES  whitened reference set for the filter, FP32, one contiguous block per tile of
-//          TILE_REFS reference rows: (d+1) rows of TILE_REFS floats, row 0 holds
+//          tile_refs(d) reference rows: (d+1) rows of tile_refs(d) floats, row 0 holds
 //          h_j = -|y_j|^2/2, row c+1 holds coordinate c.  A tile is one TMA bulk copy.
 //   CAND   candidate indices int32 [ref_chunks][list_len][nq_pad] and final thresholds
 //          float [ref_chunks][nq_pad] written by the filter, read by the re-rank
@@ -15,7 +15,8 @@
 
 namespace mce {
 
-constexpr int TILE_REFS = 128;        // reference rows per TMA tile
+// reference rows per TMA tile: 256 while a tile stays <= 11.5 KB (ndim <= 10), else 128
+__host__ __device__ constexpr int tile_refs(int d) { return d <= 10 ? 256 : 128; }
 constexpr int FILTER_THREADS = 128;   // threads per filter CTA (4 warps)
 constexpr int FILTER_STAGES = 4;      // TMA ring depth
 constexpr int KCAP = 16;              // == MCE_MAX_NEIGHBOURS

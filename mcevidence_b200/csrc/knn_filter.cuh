@@ -5,9 +5,9 @@
 //
 // Work decomposition: one CTA = one (query block, reference chunk) unit.  A query block is
 // FILTER_THREADS * TQ whitened queries; each thread keeps TQ queries (TQ*D floats) in
-// registers for the whole unit.  The reference chunk is streamed as tiles of TILE_REFS rows
+// registers for the whole unit.  The reference chunk is streamed as tiles of tile_refs(D) rows
 // through a FILTER_STAGES-deep shared-memory ring filled by TMA bulk copies
-// (cp.async.bulk + mbarrier complete_tx; one contiguous (D+1)*TILE_REFS*4-byte block per tile).
+// (cp.async.bulk + mbarrier complete_tx; one contiguous (D+1)*tile_refs(D)*4-byte block per tile).
 // Slots are handed back through per-slot "empty" mbarriers (one arrival per warp), so there is
 // no CTA-wide barrier in the main loop and warps drift freely by up to two tiles.
 //
@@ -82,7 +82,7 @@ static __device__ __noinline__ float list_insert(float* ls, int* li, int len, fl
 // Ring depth: 8 tiles while they fit 48 KB, else 4.  In SYNC mode the CTA barrier is paid once
 // per group of NS/2 tiles (the group just read is refilled while the other group is consumed).
 __host__ __device__ constexpr int filter_stages(int d, int tq) {
-    return (tq <= 2 && (d + 1) * TILE_REFS * 4 * 8 <= 48 * 1024) ? 8 : FILTER_STAGES;   // wider register tiles keep occupancy instead
+    return (tq <= 2 && (d + 1) * tile_refs(d) * 4 * 8 <= 48 * 1024) ? 8 : FILTER_STAGES;   // wider register tiles keep occupancy instead
 }
 
 // MODE 0: free-running warps (per-slot empty mbarriers); 1: CTA barrier per tile group;
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
     constexpr bool PF = MODE >= 2 && PACKED;
     constexpr int PFD = PF ? (MODE - 1 < D ? MODE - 1 : D) : 1;   // prefetched coordinate rows
     constexpr int NT = FILTER_THREADS;
-    constexpr int TJ = TILE_REFS;
+    constexpr int TJ = tile_refs(D);
     constexpr int NS = filter_stages(D, TQ);
     constexpr int G = NS / 2;   // tiles per barrier group (SYNC mode)
     constexpr int TILE_FLOATS = (D + 1) * TJ;
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
 template <int D, int TQ, int TR, bool PACKED, int MODE>
 struct FilterInst {
     static size_t smem_bytes(int list_len) {
-        return (size_t)filter_stages(D, TQ) * (D + 1) * TILE_REFS * sizeof(float) + 2 * filter_stages(D, TQ) * sizeof(uint64_t) +
+        return (size_t)filter_stages(D, TQ) * (D + 1) * tile_refs(D) * sizeof(float) + 2 * filter_stages(D, TQ) * sizeof(uint64_t) +
                (size_t)TQ * list_len * FILTER_THREADS * (sizeof(float) + sizeof(int));
     }
     static int query(int list_len, int* qpc, int* smem, int* ctas) {

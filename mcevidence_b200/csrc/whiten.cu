@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(128) whiten_kernel(Segment x, int d, const dou
     for (int e = threadIdx.x; e < d; e += blockDim.x) smu[e] = mu ? mu[e] : 0.0;
     __syncthreads();
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int TJ = tile_refs(d);
     float rn = 0.f;
     if (row < nrows_padded) {
         const bool valid = row < x.n;
@@ -176,9 +177,9 @@ __global__ void __launch_bounds__(128) whiten_kernel(Segment x, int d, const dou
         float* tb = nullptr;
         int j = 0;
         if (tiles) {
-            const long long tile = row / TILE_REFS;
-            j = (int)(row - tile * TILE_REFS);
-            tb = tiles + tile * (long long)((d + 1) * TILE_REFS);
+            const long long tile = row / TJ;
+            j = (int)(row - tile * TJ);
+            tb = tiles + tile * (long long)((d + 1) * TJ);
         }
         double n2 = 0.0;
         for (int c = 0; c < d; ++c) {
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(128) whiten_kernel(Segment x, int d, const dou
                 for (int a = 0; a < d; ++a) y += (x.at(xrow, a) - smu[a]) * sw[a * d + c];
                 y64[row * d + c] = y;
             }
-            if (tb) tb[(c + 1) * TILE_REFS + j] = (float)y;
+            if (tb) tb[(c + 1) * TJ + j] = (float)y;
             n2 += y * y;
         }
         if (tb) tb[j] = valid ? (float)(-0.5 * n2) : -INFINITY;   // row 0: h_j = -|y_j|^2 / 2
@@ -221,7 +222,8 @@ void launch_covariance(const Segment& a, const Segment& b, int d, const CovWorks
 void launch_whiten(const Segment& x, int d, const double* W, const double* mu, double* y64, float* tiles,
                    unsigned int* rmax_bits, cudaStream_t st, int* launches) {
     long long nrows = x.n;
-    if (tiles) nrows = (x.n + TILE_REFS - 1) / TILE_REFS * TILE_REFS;
+    const int TJ = tile_refs(d);
+    if (tiles) nrows = (x.n + TJ - 1) / TJ * TJ;
     if (nrows == 0) return;
     const int threads = 128;
     const long long grid = (nrows + threads - 1) / threads;

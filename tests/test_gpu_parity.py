@@ -104,6 +104,17 @@ def test_strided_rows_and_ndim_prefix(ctx):
     np.testing.assert_array_equal(dk, od)
 
 
+def test_very_wide_rows_use_pitched_copy(ctx):
+    """ld > 16 d: the host copy packs the first ndim columns (cudaMemcpy2D) instead of moving whole rows."""
+    rng = np.random.default_rng(11)
+    wide = rng.normal(size=(1200, 40))
+    for arr in (wide, wide.astype(np.float32)):
+        dk, ix, _ = ctx.knn(arr, 3, ndim=2, W=np.eye(2))
+        od, oi = oracle_knn(np.ascontiguousarray(arr[:, :2]).astype(np.float64), 3)
+        np.testing.assert_array_equal(ix, oi)
+        np.testing.assert_array_equal(dk, od)
+
+
 @pytest.mark.parametrize('n,d,kmax,cross', [(4000, 5, 4, False), (6000, 10, 4, False), (6000, 10, 4, True),
                                             (5000, 20, 8, False), (4000, 27, 4, True), (3000, 3, 2, False),
                                             (700, 2, 1, False), (900, 12, 16, False)])

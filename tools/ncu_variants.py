@@ -29,7 +29,7 @@ ctx = _lib.Context(0)
 ctx.set_option('ref_chunks', a.chunks)
 for c, tail in [(c, t) for c in a.cfg for t in a.tail]:
     ctx.set_option('tail_chunks', tail)
-    parts = [int(x) for x in c.split(',')]
+    parts = [-1, -1, -1, -1] if c == 'auto' else [int(x) for x in c.split(',')]
     tq, tr, pk = parts[:3]
     sy = parts[3] if len(parts) > 3 else -1
     ctx.set_option('filter_tq', tq); ctx.set_option('filter_tr', tr); ctx.set_option('filter_packed', pk)
