@@ -44,9 +44,9 @@ WORKLOADS = {
 }
 FP32_PEAK_THEORETICAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.4: SMs x lanes x 2 FLOP x max clock
 # dram__bytes_read.sum + dram__bytes_write.sum of one K2 launch from the ncu --set full capture of this command
-# (profiles/r01_filter_ncu_raw_default.csv: 135.9 MB read + 25.9 MB written; algorithmic: 44 MB tiles + 80 MB
+# (profiles/r01_filter_ncu_raw_final.csv: 148.7 MB read + 31.2 MB written; algorithmic: 44 MB tiles + 80 MB
 # queries + ~24 MB candidate lists -- the reference set is streamed from L2, not from HBM)
-NCU_DRAM_BYTES_PER_LAUNCH = {('cfg2', 1): 161.8e6}
+NCU_DRAM_BYTES_PER_LAUNCH = {('cfg2', 1): 179.9e6}
 METRIC = 'knn_pair_dists_per_s'
 UNIT = 'pair-dists/s'
 
