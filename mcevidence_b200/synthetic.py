@@ -63,7 +63,7 @@ def gaussian_chain(nsamples, ndim, seed=0, inflate=1.1, offset=0.0, mean_shift=0
 
 #: parameter names used for CosmoMC-shaped synthetic roots: six cosmological
 #: names the reference recognises (`MCEvidence.py:84-86`) followed by nuisance ones.
-COSMO_NAMES = ['omegabh2', 'omegach2', 'theta', 'tau', 'logA', 'ns']
+COSMO_NAMES = ['omegabh2', 'omegach2', 'theta', 'tau', 'logA', 'ns', 'omegak', 'mnu', 'nnu']
 NUISANCE_NAMES = ['calPlanck', 'acib217', 'xi', 'asz143', 'aps100', 'aps143',
                   'aps217', 'aksz', 'kgal100', 'kgal143']
 
@@ -78,6 +78,7 @@ def write_cosmomc_root(root, nchains=4, nrows=6700, ncosmo=6, nnuis=4, seed=0,
     """
     names = COSMO_NAMES[:ncosmo] + NUISANCE_NAMES[:nnuis]
     ndim = len(names)
+    fixed = tuple(f for f in fixed if f not in names)
     os.makedirs(os.path.dirname(os.path.abspath(root)), exist_ok=True)
     for ic in range(nchains):
         chain, _ = gaussian_chain(nrows + 17 * ic, ndim, seed=seed * 1000 + ic + 1,
@@ -91,3 +92,28 @@ def write_cosmomc_root(root, nchains=4, nrows=6700, ncosmo=6, nnuis=4, seed=0,
         for nm in fixed:
             fh.write('%-12s %.6e %.6e\n' % (nm, 3.046, 3.046))
     return names, (hi - lo) ** ncosmo
+
+
+def write_cosmomc_grid(rootdir, datasets=('plikHM_TT_lowTEB', 'plikHM_TT_lowTEB_post_BAO'),
+                       models=(('base', 6), ('base_omegak', 7), ('base_mnu', 7)), nchains=2, nrows=900, seed=0):
+    """A miniature ``COM_CosmoParams_fullGrid_R2.00`` tree: ``<rootdir>/<model>/<data_dir>/<model>_<data>_<i>.txt``
+    plus ``.ranges`` and ``.paramnames`` (with a derived ``H0*`` column appended), as read by
+    ``planck_mcevidence.py``.  ``models`` lists ``(name, number of cosmological parameters)``.
+    Returns ``{(data, model): (root, names, prior volume)}``."""
+    out = {}
+    for idd, dd in enumerate(datasets):
+        for imm, (mm, ncosmo) in enumerate(models):
+            root = os.path.join(rootdir, mm, dd.split('_post_')[0], '%s_%s' % (mm, dd))
+            names, vol = write_cosmomc_root(root, nchains=nchains, nrows=nrows + 37 * imm, ncosmo=ncosmo, nnuis=3,
+                                            seed=seed + 10 * idd + imm)
+            for ic in range(nchains):                       # append a derived H0* column
+                f = '%s_%d.txt' % (root, ic + 1)
+                c = np.loadtxt(f)
+                h0 = 67.0 + 3.0 * c[:, 2] + 0.5 * c[:, 3]
+                np.savetxt(f, np.column_stack((c, h0)), fmt='%.10e')
+            with open(root + '.paramnames', 'w') as fh:
+                for nm in names:
+                    fh.write('%s\t%s\n' % (nm, nm))
+                fh.write('H0*\tH_0\n')
+            out[(dd, mm)] = (root, names, vol)
+    return out

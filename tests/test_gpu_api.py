@@ -99,3 +99,41 @@ def test_grid_of_chains_batched():
     bad = np.column_stack((np.ones(50), np.zeros(50), np.ones((50, 2))))      # constant columns: singular covariance
     with pytest.raises(_lib.MCEError, match='problem 1'):
         evidence_many([chains[0], bad], kmax=2)
+
+
+def test_planck_grid_driver(tmp_path):
+    """The grid driver end to end on a miniature CosmoMC grid: tables, csv files and values vs the oracle."""
+    import pandas as pd
+    import planck_mcevidence as P
+    from mcevidence_b200.synthetic import write_cosmomc_grid
+    rootdir, out = str(tmp_path / 'grid'), str(tmp_path / 'out')
+    grid = write_cosmomc_grid(rootdir, nchains=2, nrows=700)
+    dsets = ['plikHM_TT_lowTEB', 'plikHM_TT_lowTEB_post_BAO']
+    P.main(['--rootdir', rootdir, '-o', out, '-k', '2', '-b', '0.3', '-v', '0', '--datasets'] + dsets)
+    vol_base = {dd: grid[(dd, 'base')][2] for dd in dsets}
+    for dd in dsets:
+        df = pd.read_csv(os.path.join(out, 'AllChains', 'csv', 'mce_%s.csv' % dd), index_col=0)
+        assert list(df.index) == ['base', 'base_omegak', 'base_mnu']
+        assert list(df.columns) == ['AllChains', 'delta_lnE_k1', 'PriorVol', 'ndim', 'N_read', 'N_used']
+        for mm in df.index:
+            root, names, vol = grid[(dd, mm)]
+            chains = [np.loadtxt('%s_%d.txt' % (root, i + 1)) for i in range(2)]
+            burned = np.concatenate([c[int(len(c) * 0.3):] for c in chains])
+            nd = int(df.loc[mm, 'ndim'])
+            want = O.evidence(burned[:, 2:], -burned[:, 1], burned[:, 0], nd, 2, priorvolume=vol / vol_base[dd],
+                              knn='brute')
+            assert abs(df.loc[mm, 'AllChains'] - want[0]) < 1e-8
+            assert np.isclose(df.loc[mm, 'PriorVol'], vol / vol_base[dd])
+        assert np.isclose(df['delta_lnE_k1'].max(), 0.0)
+    assert os.path.exists(os.path.join(out, 'AllChains', 'mce_planck_fullgrid.txt'))
+    assert os.path.exists(os.path.join(out, 'AllChains', 'delta_lnE_all.txt'))
+    # per-chain run with the H0 importance weight: Mean / Err columns (planck_mcevidence.py:366-372)
+    P.main(['--rootdir', rootdir, '-o', out, '-nc', '2', '-nd', '1', '-v', '0', '--h0prior', '--datasets'] + dsets)
+    df = pd.read_csv(os.path.join(out, 'SingleChains', 'csv', 'mce_%s.csv' % dsets[0]), index_col=0)
+    assert list(df.columns)[:5] == ['chain1', 'chain2', 'Mean_lnE_k1', 'Err_lnE_k1', 'delta_lnE_k1']
+    root = grid[(dsets[0], 'base')][0]
+    c = np.loadtxt(root + '_1.txt')
+    aw = c[:, 0] * np.exp(-0.5 * ((c[:, 2 + 9] - 73.24) / 1.74) ** 2)
+    want = O.evidence(c[:, 2:], -c[:, 1], c[:, 0], 6, 2, adjusted_weights=aw, knn='brute')
+    assert abs(df.loc['base', 'chain1'] - want[0]) < 1e-8
+    assert np.isclose(df.loc['base', 'Err_lnE_k1'], df.loc['base', ['chain1', 'chain2']].std() / np.sqrt(2.0))

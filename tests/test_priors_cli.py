@@ -88,3 +88,25 @@ def test_synthetic_cosmomc_root(tmp_path):
     info = priors.params_info(root, cosmo=True)
     assert info['ndim'] == 6 and np.isclose(info['volume'], vol)
     assert priors.params_info(root, cosmo=False)['ndim'] == len(names)
+
+
+def test_grid_driver_discovery_and_flags(tmp_path):
+    """planck_mcevidence.py: the reference's flags, and model discovery in table order on a miniature grid."""
+    import planck_mcevidence as P
+    from mcevidence_b200.synthetic import write_cosmomc_grid
+    a = P.build_parser().parse_args(['-k', '3', '-nc', '4', '-nd', '2', '-nm', '5', '-b', '0.3', '-t', '0.5',
+                                     '-o', 'out', '--N', 'xx', '-v', '0'])
+    assert (a.kmax, a.nchain, a.ndata, a.nmodel, a.burnfrac, a.thinfrac, a.outdir, a.name, a.verbose) == \
+        (3, 4, 2, 5, 0.3, 0.5, 'out', 'xx', 0)
+    d = P.build_parser().parse_args([])
+    assert (d.kmax, d.nchain, d.outdir, d.name) == (2, 0, 'planck_mce_fullGrid_R2_H0Reiss2016', 'mce')
+    assert P.build_parser().parse_args(['--burnin', '0.2', '--thinfrac', '0.1']).burnfrac == 0.2
+    assert len(P.DATASETS) == 31 and len(P.MODELS) == 22 and P.MODELS[0] == 'base'
+    grid = write_cosmomc_grid(str(tmp_path / 'grid'), nrows=50)
+    paths, names = P.avail_model_list(str(tmp_path / 'grid'), 'plikHM_TT_lowTEB')
+    assert names == ['base', 'base_omegak', 'base_mnu']                  # the reference's model order
+    assert paths[0] == grid[('plikHM_TT_lowTEB', 'base')][0]
+    assert P.avail_model_list(str(tmp_path / 'grid'), 'plikHM_TT_lowTEB_post_BAO', nmax=2)[1] == ['base', 'base_omegak']
+    assert P.avail_model_list(str(tmp_path / 'grid'), 'nothing_here')[0] == []
+    assert P.h0_column(paths[0]) == 9                                     # 6 cosmological + 3 nuisance columns, then H0*
+    assert priors.params_info(paths[1], cosmo=True)['ndim'] == 7
