@@ -129,6 +129,43 @@ struct Run {
     mce_stats* stats;
 };
 
+// Work decomposition model (calibrated on B200, profiles/r01_filter_variants.md).  Query blocks [0, nfull)
+// scan the whole reference set as one unit (all full waves of blocks); blocks [nfull, nqblocks) are split
+// into `chunks` reference ranges so that the last wave is short; small problems (less than one wave) are
+// split throughout.  Every split restarts the top-L lists, and a list insertion costs as much as kappa
+// pair evaluations, so
+//     unit(m) = m + kappa L ln(m / L)                             pair-equivalents per query of an m-reference unit
+//     T(c)    = nfull/slots unit(n_ref) + ceil(rem c / SMs) / ctas unit(n_ref / c)
+// (the tail is counted per SM: an SM that receives one unit more than its neighbours finishes later)
+// Returns T * (queries resident per SM) / (relative pair rate): comparable between tile shapes.
+struct SplitPlan { int nfull, chunks; double cost; };
+SplitPlan plan_split(long long nqblocks, int sm_count, int qpc, int ctas, long long n_ref, int list_len, int d,
+                     bool wide, int max_chunks) {
+    const long long slots = (long long)sm_count * ctas;
+    const double kappa = (wide ? 500.0 : 250.0) * 11.5 / (d + 1.5);
+    auto unit = [&](double m) { return m + kappa * list_len * log(fmax(m / list_len, 2.0)); };
+    const long long nf = (nqblocks / slots) * slots;
+    const long long rem = nqblocks - nf;
+    SplitPlan best{(int)nf, 1, 1e300};
+    const double head = (double)(nf / slots) * unit((double)n_ref);
+    // less than one wave of blocks: split at least until every CTA slot has a unit (a lone CTA on an SM runs
+    // far below a quarter of the SM's rate, which the per-SM count above does not capture)
+    int c_min = 1;
+    if (nf == 0 && rem < slots) c_min = (int)((slots + rem - 1) / rem);
+    if (c_min > max_chunks) c_min = max_chunks;
+    for (int cc = c_min; cc <= max_chunks; ++cc) {
+        const double tail = rem ? (double)((rem * cc + sm_count - 1) / sm_count) / ctas * unit((double)n_ref / cc) : 0.0;
+        const double t = head + tail;
+        if (t < best.cost) {
+            best.cost = t;
+            best.chunks = cc;
+        }
+        if (!rem) break;
+    }
+    best.cost *= (double)qpc * ctas / (wide ? 1.05 : 1.0);
+    return best;
+}
+
 int run_problem(mce_ctx* c, const Run& r) {
     const mce_problem& p = *r.p;
     int rc = validate(&p, r.evidence);
@@ -302,14 +339,22 @@ int run_problem(mce_ctx* c, const Run& r) {
     if (c->opt_packed >= 0) cfg.packed = c->opt_packed;
     if (c->opt_sync >= 0) cfg.sync = c->opt_sync;
     int qpc = 0, smem = 0, ctas = 0;
+    const int max_chunks = ntiles / 4 > 1 ? (ntiles / 4 > 64 ? 64 : ntiles / 4) : 1;
     if (c->opt_tq <= 0 && c->opt_tr <= 0 && c->opt_packed < 0 && c->opt_sync < 0 && d <= 16) {
-        // Low ndim, large problems: four queries per thread (half the shared-memory traffic per FMA, two-row
-        // prefetch) is 2-8 % faster once its 512-query blocks fill at least one wave; below that the
-        // 256-query blocks of the default fill the GPU with fewer reference splits.
+        // Low ndim: four queries per thread (half the shared-memory traffic per FMA, two-row prefetch) is
+        // 2-11 % faster when its 512-query blocks fill the GPU; the modelled cost decides (small inputs
+        // fill the GPU with fewer reference splits using the 256-query blocks of the default).
         FilterConfig wide{4, 8, 1, 3};
-        int q4 = 0, s4 = 0, c4 = 0;
-        if (filter_query(d, wide, list_len, &q4, &s4, &c4) == 0 && nq / q4 >= (long long)c->sm_count * c4) cfg = wide;
-        else cudaGetLastError();
+        int qn = 0, sn = 0, cn = 0, q4 = 0, s4 = 0, c4 = 0;
+        if (filter_query(d, cfg, list_len, &qn, &sn, &cn) == 0 && filter_query(d, wide, list_len, &q4, &s4, &c4) == 0) {
+            const SplitPlan pn = plan_split((nq + qn - 1) / qn, c->sm_count, qn, cn, n_ref, list_len, d,
+                                            false, max_chunks);
+            const SplitPlan pw = plan_split((nq + q4 - 1) / q4, c->sm_count, q4, c4, n_ref, list_len, d,
+                                            true, max_chunks);
+            if (pw.cost < pn.cost) cfg = wide;
+        } else {
+            cudaGetLastError();
+        }
     }
     if (filter_query(d, cfg, list_len, &qpc, &smem, &ctas) != 0) {
         cudaGetLastError();
@@ -324,16 +369,7 @@ int run_problem(mce_ctx* c, const Run& r) {
     }
     const int nqblocks = (int)((nq + qpc - 1) / qpc);
     const long long nq_pad = (long long)nqblocks * qpc;
-    // Work decomposition.  Every list insertion costs about as much as ~200 pair evaluations (at d = 10;
-    // less for larger d) and every split of the reference set restarts the lists, so whole-set units are
-    // preferred: blocks [0, nfull) run as whole-set units (all full waves of query blocks), blocks
-    // [nfull, nqblocks) are split into `chunks` units to keep the last wave short; small problems
-    // (less than one wave of query blocks) are split throughout.  `chunks` minimises a simple cost
-    // model calibrated on B200 (profiles/r01_filter_variants.md):
-    //   unit(m) = m + kappa L ln(m / L)                      pair-equivalents per query of an m-reference unit
-    //   T(c)    = nfull/slots unit(n_ref) + (max(rem c / slots, 1) + 1/2) unit(n_ref / c)
     const long long slots = (long long)c->sm_count * ctas;
-    const int max_chunks = ntiles / 4 > 1 ? (ntiles / 4 > 64 ? 64 : ntiles / 4) : 1;
     int chunks = 1, nfull = nqblocks;
     if (c->opt_chunks > 0) {
         chunks = c->opt_chunks;      // uniform split (tuning / tests)
@@ -342,21 +378,9 @@ int run_problem(mce_ctx* c, const Run& r) {
         chunks = c->opt_tail;        // whole-set units for the full waves, forced split of the remainder
         nfull = (int)((nqblocks / slots) * slots);
     } else {
-        const double kappa = 200.0 * 11.5 / (d + 1.5);
-        auto unit = [&](double m) { return m + kappa * list_len * log(fmax(m / list_len, 2.0)); };
-        const long long nf = (nqblocks / slots) * slots;
-        const long long rem = nqblocks - nf;
-        nfull = (int)nf;
-        if (rem > 0) {
-            double best = 1e300;
-            for (int cc = 1; cc <= max_chunks; ++cc) {
-                const double t = (fmax((double)rem * cc / slots, 1.0) + 0.5) * unit((double)n_ref / cc);
-                if (t < best) {
-                    best = t;
-                    chunks = cc;
-                }
-            }
-        }
+        const SplitPlan pl = plan_split(nqblocks, c->sm_count, qpc, ctas, n_ref, list_len, d, cfg.tq >= 4, max_chunks);
+        chunks = pl.chunks;
+        nfull = pl.nfull;
     }
     if (chunks > ntiles) chunks = ntiles;
     const int tiles_per_chunk = (ntiles + chunks - 1) / chunks;

@@ -20,6 +20,7 @@ ap.add_argument('--d', type=int, default=10)
 ap.add_argument('--kmax', type=int, default=4)
 ap.add_argument('--chunks', type=int, default=-1)
 ap.add_argument('--reps', type=int, default=1)
+ap.add_argument('--qn', type=int, default=0, help='search only the first qn query rows (a rank shard)')
 ap.add_argument('--tail', type=int, nargs='*', default=[-1])
 ap.add_argument('--cfg', nargs='+', default=['2,8,1'])
 a = ap.parse_args()
@@ -36,7 +37,7 @@ for c, tail in [(c, t) for c in a.cfg for t in a.tail]:
     ctx.set_option('filter_sync', sy)
     best = None
     for _ in range(a.reps):
-        out = ctx.evidence(s, l, w, a.kmax, log_sum_w=math.log(w.sum()))
+        out = ctx.evidence(s, l, w, a.kmax, log_sum_w=math.log(w.sum()), q_range=(0, a.qn) if a.qn else None)
         st = out['stats']
         if best is None or st['ms_filter'] < best['ms_filter']:
             best = st
