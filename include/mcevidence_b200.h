@@ -72,7 +72,8 @@ typedef struct mce_problem {
     /* Whitening y = (x - mu) W.  W == NULL: the library estimates the unweighted, ddof=1 covariance of
        query U ref (np.cov, MCEvidence.py:865), factors it (Cholesky) and sets log J = 0.5 log det C (:877).
        Otherwise W is d x d row-major (for the reference's own factor: eVec / sqrt(eVal), :844-847),
-       W_ref optionally a different matrix for the ref set (covtype='single', :1080-1086), mu may be NULL (0). */
+       W_ref optionally a different matrix for the ref set (covtype='single', :1080-1086), mu may be NULL (0).
+       W, W_ref and mu are always HOST pointers, also with MCE_FLAG_DEVICE_PTRS. */
     const double *W;
     const double *W_ref;
     const double *mu;

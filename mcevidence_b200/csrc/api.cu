@@ -387,9 +387,13 @@ int run_problem(mce_ctx* c, const Run& r) {
     chunks = (ntiles + tiles_per_chunk - 1) / tiles_per_chunk;
     if (chunks == 1) nfull = nqblocks;
 
-    rc = c->cand_idx.ensure((size_t)chunks * list_len * nq_pad * sizeof(int));
+    // candidate planes: chunk 0 for every query, chunks 1.. only for the queries of the split blocks
+    const long long tail_q0 = (long long)nfull * qpc;
+    const long long ntail_pad = (long long)(nqblocks - nfull) * qpc;
+    const size_t cand_elems = (size_t)nq_pad + (size_t)(chunks - 1) * (size_t)ntail_pad;
+    rc = c->cand_idx.ensure(cand_elems * list_len * sizeof(int));
     if (rc) return rc;
-    rc = c->cand_th.ensure((size_t)chunks * nq_pad * sizeof(float));
+    rc = c->cand_th.ensure(cand_elems * sizeof(float));
     if (rc) return rc;
     rc = c->flagged.ensure((size_t)nq * sizeof(int));
     if (rc) return rc;
@@ -403,6 +407,8 @@ int run_problem(mce_ctx* c, const Run& r) {
         fp.q_begin = qb;
         fp.q_end = qe;
         fp.nq_pad = nq_pad;
+        fp.ntail_pad = ntail_pad;
+        fp.tail_q0 = tail_q0;
         fp.self_offset = 0;
         fp.self_exclude = cross ? 0 : 1;
         fp.ntiles = ntiles;
@@ -449,6 +455,8 @@ int run_problem(mce_ctx* c, const Run& r) {
     rp.q_begin = qb;
     rp.q_end = qe;
     rp.nq_pad = nq_pad;
+    rp.ntail_pad = ntail_pad;
+    rp.tail_q0 = tail_q0;
     rp.n_ref = n_ref;
     rp.self_offset = 0;
     rp.self_exclude = cross ? 0 : 1;

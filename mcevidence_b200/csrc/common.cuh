@@ -6,8 +6,9 @@
 //   TILES  whitened reference set for the filter, FP32, one contiguous block per tile of
 //          tile_refs(d) reference rows: (d+1) rows of tile_refs(d) floats, row 0 holds
 //          h_j = -|y_j|^2/2, row c+1 holds coordinate c.  A tile is one TMA bulk copy.
-//   CAND   candidate indices int32 [ref_chunks][list_len][nq_pad] and final thresholds
-//          float [ref_chunks][nq_pad] written by the filter, read by the re-rank
+//   CAND   candidate indices int32 and final thresholds float written by the filter, read by the
+//          re-rank: plane 0 (reference chunk 0) covers every query, [list_len][nq_pad]; planes
+//          1.. only the queries of the split blocks, [ref_chunks-1][list_len][ntail_pad]
 //   DKNN   FP64 (nq, K) ascending neighbour distances, IDX int64 (nq, K)
 #pragma once
 #include <cuda_runtime.h>
@@ -61,10 +62,12 @@ void launch_whiten(const Segment& x, int d, const double* W, const double* mu, d
 struct FilterParams {
     const double* yq;        // whitened queries FP64 (row r at yq + r*d); rows [q_begin, q_end) are searched
     const float*  tiles;     // reference tiles
-    int*   cand_idx;         // [ref_chunks][list_len][nq_pad]
-    float* cand_th;          // [ref_chunks][nq_pad]
+    int*   cand_idx;         // chunk 0: [list_len][nq_pad]; chunk r >= 1: + cand_off(r, e) + (ql - tail_q0)
+    float* cand_th;          // chunk 0: [nq_pad];           chunk r >= 1: nq_pad + (r-1) ntail_pad + (ql - tail_q0)
     long long q_begin, q_end;
     long long nq_pad;
+    long long ntail_pad;     // padded number of queries in the split blocks
+    long long tail_q0;       // first local query id of the split blocks (= nfull * queries per block)
     long long self_offset;   // auto mode: reference index of query row r is r + self_offset; cross mode: any
     int self_exclude;        // 1 in auto mode
     int ntiles;
@@ -76,6 +79,16 @@ struct FilterParams {
     int list_len;
     int d;
 };
+// element offsets into the candidate buffers (shared by the filter and the re-rank)
+__host__ __device__ __forceinline__ long long cand_idx_offset(int r, int e, long long ql, int list_len, long long nq_pad,
+                                                              long long ntail_pad, long long tail_q0) {
+    return r == 0 ? (long long)e * nq_pad + ql
+                  : (long long)list_len * nq_pad + ((long long)(r - 1) * list_len + e) * ntail_pad + (ql - tail_q0);
+}
+__host__ __device__ __forceinline__ long long cand_th_offset(int r, long long ql, long long nq_pad, long long ntail_pad,
+                                                             long long tail_q0) {
+    return r == 0 ? ql : nq_pad + (long long)(r - 1) * ntail_pad + (ql - tail_q0);
+}
 struct FilterConfig { int tq, tr, packed, sync; };
 // Returns 0 and fills grid/smem/ctas_per_sm on success, -1 if (d, cfg) has no instantiation.
 int filter_query(int d, const FilterConfig& cfg, int list_len, int* queries_per_cta, int* smem_bytes,
@@ -89,6 +102,7 @@ struct RerankParams {
     const double* yr;        // whitened references
     const int*   cand_idx;
     const float* cand_th;
+    long long ntail_pad, tail_q0;   // candidate planes of chunks >= 1 (see FilterParams)
     const unsigned int* rmax_bits;
     double*    dknn;         // (nq, out_ld) ; neighbours written at column out_col0..
     long long* idx;

@@ -372,9 +372,9 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
     for (int t = 0; t < TQ; ++t) {
         const long long ql = ql0 + (long long)t * NT;
         if (ql < nq) {
-            p.cand_th[(long long)rchunk * p.nq_pad + ql] = th[t];
+            p.cand_th[cand_th_offset(rchunk, ql, p.nq_pad, p.ntail_pad, p.tail_q0)] = th[t];
             for (int e = 0; e < L; ++e)
-                p.cand_idx[((long long)rchunk * L + e) * p.nq_pad + ql] = li[(t * L + e) * NT + tid];
+                p.cand_idx[cand_idx_offset(rchunk, e, ql, L, p.nq_pad, p.ntail_pad, p.tail_q0)] = li[(t * L + e) * NT + tid];
         }
     }
 }

@@ -127,9 +127,9 @@ __global__ void __launch_bounds__(128) rerank_kernel(const RerankParams p) {
     float thmax = -CUDART_INF_F;
     const int nchunks = ql < p.nfull_queries ? 1 : p.ref_chunks;
     for (int r = 0; r < nchunks; ++r) {
-        thmax = fmaxf(thmax, p.cand_th[(long long)r * p.nq_pad + ql]);
+        thmax = fmaxf(thmax, p.cand_th[cand_th_offset(r, ql, p.nq_pad, p.ntail_pad, p.tail_q0)]);
         for (int e = 0; e < p.list_len; ++e) {
-            const int id = p.cand_idx[((long long)r * p.list_len + e) * p.nq_pad + ql];
+            const int id = p.cand_idx[cand_idx_offset(r, e, ql, p.list_len, p.nq_pad, p.ntail_pad, p.tail_q0)];
             if (id < 0) continue;
             top.push(sq_dist_seq(q, p.yr + (long long)id * d, d), id);
         }
