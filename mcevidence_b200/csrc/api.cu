@@ -401,6 +401,7 @@ int run_problem(mce_ctx* c, const Run& r) {
     if (!exact_only) {
         FilterParams fp;
         fp.yq = yq_base;
+        fp.status = &ds->status;
         fp.tiles = c->tiles.as<float>();
         fp.cand_idx = c->cand_idx.as<int>();
         fp.cand_th = c->cand_th.as<float>();
@@ -444,6 +445,7 @@ int run_problem(mce_ctx* c, const Run& r) {
     }
     RerankParams rp;
     rp.yq = yq_base;
+    rp.status = &ds->status;
     rp.yr = c->yr.as<double>();
     rp.cand_idx = c->cand_idx.as<int>();
     rp.cand_th = c->cand_th.as<float>();

@@ -62,6 +62,7 @@ void launch_whiten(const Segment& x, int d, const double* W, const double* mu, d
 struct FilterParams {
     const double* yq;        // whitened queries FP64 (row r at yq + r*d); rows [q_begin, q_end) are searched
     const float*  tiles;     // reference tiles
+    const int* status;       // device flag of K0: non-zero (covariance not positive definite) -> return at once
     int*   cand_idx;         // chunk 0: [list_len][nq_pad]; chunk r >= 1: + cand_off(r, e) + (ql - tail_q0)
     float* cand_th;          // chunk 0: [nq_pad];           chunk r >= 1: nq_pad + (r-1) ntail_pad + (ql - tail_q0)
     long long q_begin, q_end;
@@ -100,6 +101,7 @@ void filter_default_config(int d, int list_len, FilterConfig* cfg);
 struct RerankParams {
     const double* yq;        // whitened queries
     const double* yr;        // whitened references
+    const int*   status;     // as in FilterParams: skip all work after a failed factorisation
     const int*   cand_idx;
     const float* cand_th;
     long long ntail_pad, tail_q0;   // candidate planes of chunks >= 1 (see FilterParams)

@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
     int* li = reinterpret_cast<int*>(ls + TQ * L * NT);
 
     const int tid = threadIdx.x;
+    if (*p.status != 0) return;   // the whitening matrix is garbage: the host reports the error
     // unit -> (query block, reference chunk): the first nfull blocks are whole-set units, the
     // remaining blocks are split so that the last wave of the grid is short
     int qblock, rchunk, t0, t1;

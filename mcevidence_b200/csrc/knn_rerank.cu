@@ -114,7 +114,7 @@ __device__ __forceinline__ void write_row(const RerankParams& p, long long ql, c
 __global__ void __launch_bounds__(128) rerank_kernel(const RerankParams p) {
     const long long ql = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nq = p.q_end - p.q_begin;
-    if (ql >= nq) return;
+    if (ql >= nq || *p.status != 0) return;
     if (p.flag_all) {
         p.flagged[ql] = (int)ql;
         if (ql == 0) *p.nflagged = (int)nq;
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_rescan_kernel(const Reran
     __shared__ long long wi;
     __shared__ int wowner;
     __shared__ double sq[MAX_DIM];
-    const int nfl = *p.nflagged;
+    const int nfl = *p.status != 0 ? 0 : *p.nflagged;
     const int d = p.d;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nseg = exact_segments(nfl, gridDim.x);
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_rescan_kernel(const Reran
 // Merge the per-segment lists of each flagged row (no-op when rows were not segmented).
 __global__ void __launch_bounds__(128) exact_merge_kernel(const RerankParams p, int rescan_grid, const double* scratch_d,
                                                            const long long* scratch_i) {
-    const int nfl = *p.nflagged;
+    const int nfl = *p.status != 0 ? 0 : *p.nflagged;
     const int nseg = exact_segments(nfl, rescan_grid);
     if (nseg == 1) return;
     const int f = blockIdx.x * blockDim.x + threadIdx.x;

@@ -247,6 +247,14 @@ def test_argument_errors(ctx):
     with pytest.raises(_lib.MCEError) as ei:
         ctx.evidence(degenerate, w, w, 2)
     assert ei.value.code == _lib.ERR_NOT_POSDEF
+    # a failed factorisation must not leave the GPU scanning garbage: a large degenerate input fails fast
+    import time
+    big = np.random.default_rng(1).normal(size=(300000, 4))
+    big[:, 2] = 7.0
+    t0 = time.perf_counter()
+    with pytest.raises(_lib.MCEError):
+        ctx.evidence(big, np.zeros(300000), np.ones(300000), 3)
+    assert time.perf_counter() - t0 < 5.0
     # the context survives errors
     ctx.knn(x, 2, identity=True)
 
