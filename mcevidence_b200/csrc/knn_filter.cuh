@@ -3,25 +3,31 @@
 // Replaces the neighbour search of NearestNeighbors.kneighbors (MCEvidence.py:1104; sklearn
 // kd_tree / ArgKmin) by an exhaustive scan whose survivors are re-ranked exactly in FP64 (K3).
 //
-// Work decomposition: one CTA = one (query block, reference chunk) unit.  A query block is
+// Work decomposition: one CTA = one (query block, reference range) unit.  A query block is
 // FILTER_THREADS * TQ whitened queries; each thread keeps TQ queries (TQ*D floats) in
-// registers for the whole unit.  The reference chunk is streamed as tiles of tile_refs(D) rows
-// through a FILTER_STAGES-deep shared-memory ring filled by TMA bulk copies
-// (cp.async.bulk + mbarrier complete_tx; one contiguous (D+1)*tile_refs(D)*4-byte block per tile).
-// Slots are handed back through per-slot "empty" mbarriers (one arrival per warp), so there is
-// no CTA-wide barrier in the main loop and warps drift freely by up to two tiles.
+// registers for the whole unit.  The first `nfull` blocks scan the whole reference set as one
+// unit; the remaining blocks are split into `ref_chunks` ranges to keep the last wave short
+// (every split restarts the top-L lists, so it is used sparingly; the split is chosen by the
+// cost model in api.cu).  The range is streamed as tiles of tile_refs(D) rows through a 4- or
+// 8-slot shared-memory ring filled by TMA bulk copies (cp.async.bulk + mbarrier complete_tx;
+// one contiguous (D+1)*tile_refs(D)*4-byte block per tile).  MODE >= 1 (default): slots are
+// recycled in groups of half the ring behind one __syncthreads per group; MODE 0: per-slot
+// "empty" mbarriers (one arrival per warp) and no CTA-wide barrier.
 //
 // Ranking score: s(q, r) = q.r - |r|^2/2 = (|q|^2 - |q - r|^2) / 2, larger is closer.  The
 // accumulator is initialised with h_r = -|r|^2/2 (row 0 of the tile), so one pair costs exactly
 // D FMAs.  In the packed variant two references share one FFMA2 (fma.rn.f32x2): the query
 // coordinate is a scalar register broadcast to both halves by the instruction, the reference
-// pair comes straight out of a broadcast LDS.128.
+// pair comes straight out of a broadcast LDS.128.  MODE >= 2 prefetches the first rows of the
+// next step into registers half-way through the current one.
 //
-// Selection: each thread compares the TR scores of a step against its queries' thresholds
-// (one FSETP per pair, or-reduced to a single rarely taken branch).  Passing scores are
-// inserted into a per-(thread, query) list of list_len entries in shared memory (replace the
-// minimum, new threshold = new minimum).  A thread sees every reference of the chunk for its
-// own queries, so no cross-thread merge is needed; chunks are merged by the re-rank.
+// Selection: per step each thread takes the maximum of the TR scores of each of its queries
+// (FMNMX3) and compares it with that query's threshold (one FSETP per query, or-reduced to a
+// single rarely taken branch).  Passing scores are inserted into a per-(thread, query) list of
+// list_len entries in shared memory (replace the minimum, new threshold = new minimum).  A
+// thread sees every reference of the range for its own queries, so no cross-thread merge is
+// needed; ranges are merged by the re-rank.  In auto mode the self pair always passes and is
+// dropped by index inside the slow path, so self-exclusion costs nothing in the fast path.
 #pragma once
 #include "common.cuh"
 #include <math_constants.h>
