@@ -29,12 +29,26 @@ def assign_largest_first(sizes, world):
     return buckets
 
 
-def evidence_many(chains, kmax=2, ndim=None, priorvolume=1.0, device=0, ctx=None, group=None):
+_stream_contexts = {}
+
+
+def _contexts(device, n):
+    """``n`` independent contexts (stream + workspace each) on ``device`` for overlapping small problems."""
+    have = _stream_contexts.setdefault(device, [])
+    while len(have) < n:
+        have.append(_lib.Context(device))
+    return have[:n]
+
+
+def evidence_many(chains, kmax=2, ndim=None, priorvolume=1.0, device=0, ctx=None, group=None, nstreams=4):
     """Auto-mode log-evidence of every chain in ``chains`` (arrays ``[weight, -logL, theta...]``).
 
     ``ndim`` / ``priorvolume`` may be scalars or per-chain sequences.  Single process: all chains run
     on ``device``.  With an initialised ``torch.distributed`` group every rank must pass the same
     list; rank r computes its share and all ranks return the full list of ``logE`` arrays.
+    A rank's share is further dealt over ``nstreams`` contexts of the same GPU, each driven by its own
+    host thread through one ``mce_evidence_batch`` call (ctypes releases the GIL), so that the kernels of
+    small chains -- which cannot fill 148 SMs on their own -- overlap.
     """
     n = len(chains)
     ndims = [ndim] * n if (ndim is None or np.isscalar(ndim)) else list(ndim)
@@ -45,14 +59,26 @@ def evidence_many(chains, kmax=2, ndim=None, priorvolume=1.0, device=0, ctx=None
         import torch.distributed as dist
         rank, world = dist.get_rank(group), dist.get_world_size(group)
     mine = assign_largest_first([len(c) for c in chains], world)[rank]
-    ctx = ctx or _lib.default_context(device)
     probs = []
     for i in mine:
         c = np.asarray(chains[i], dtype=np.float64)
         nd = c.shape[1] - 2 if ndims[i] is None else int(ndims[i])
         probs.append({'query': c[:, 2:], 'logl': -c[:, 1], 'weights': c[:, 0], 'kmax': kmax, 'ndim': nd,
                       'log_sum_w': math.log(np.sum(c[:, 0])), 'log_prior_volume': math.log(pvs[i])})
-    outs = ctx.evidence_batch(probs) if probs else []          # one C call: mce_evidence_batch
+    nstreams = max(1, min(int(nstreams), len(probs) // 4)) if ctx is None else 1
+    if nstreams <= 1:
+        ctx = ctx or _lib.default_context(device)
+        outs = ctx.evidence_batch(probs) if probs else []          # one C call: mce_evidence_batch
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        lanes = assign_largest_first([len(p['weights']) for p in probs], nstreams)
+        ctxs = _contexts(device, nstreams)
+        with ThreadPoolExecutor(max_workers=nstreams) as pool:
+            parts = list(pool.map(lambda cl: cl[0].evidence_batch([probs[j] for j in cl[1]]), zip(ctxs, lanes)))
+        outs = [None] * len(probs)
+        for lane, part in zip(lanes, parts):
+            for j, o in zip(lane, part):
+                outs[j] = o
     local = {i: (o['logE'], o['var_logE'], o['stats']['ms_total']) for i, o in zip(mine, outs)}
     if world > 1:
         gathered = [None] * world

@@ -90,6 +90,12 @@ def test_grid_of_chains_batched():
     for c, le in zip(chains, loge):
         want = O.evidence(c[:, 2:], -c[:, 1], c[:, 0], c.shape[1] - 2, 2, knn='brute')
         assert np.abs(le - want).max() < 1e-9
+    # overlapped on several contexts of the same GPU: same numbers
+    many = chains * 4
+    a1, _, _ = evidence_many(many, kmax=2, nstreams=1)
+    a4, _, _ = evidence_many(many, kmax=2, nstreams=4)
+    for x, y in zip(a1, a4):
+        np.testing.assert_array_equal(x, y)
     # per-chain ndim / prior volume, and an error inside a batch names the failing problem
     loge2, _, _ = evidence_many(chains[:2], kmax=3, ndim=[4, 5], priorvolume=[2.0, 3.0])
     for c, nd, pv, le in zip(chains[:2], (4, 5), (2.0, 3.0), loge2):
@@ -98,7 +104,7 @@ def test_grid_of_chains_batched():
     from mcevidence_b200 import _lib
     bad = np.column_stack((np.ones(50), np.zeros(50), np.ones((50, 2))))      # constant columns: singular covariance
     with pytest.raises(_lib.MCEError, match='problem 1'):
-        evidence_many([chains[0], bad], kmax=2)
+        evidence_many([chains[0], bad], kmax=2, nstreams=1)
 
 
 def test_planck_grid_driver(tmp_path):

@@ -25,6 +25,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--kind', default='AllChains')
 ap.add_argument('--cpu-cells', type=int, default=6)
 ap.add_argument('--reps', type=int, default=3)
+ap.add_argument('--nstreams', type=int, default=4)
 a = ap.parse_args()
 rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
 if world > 1:
@@ -38,13 +39,13 @@ t0 = time.perf_counter()
 chains = [gaussian_chain(n, nd, seed=i, inflate=1.0, integer_weights=True, nextra=3)[0] for i, (nd, n) in enumerate(cells)]
 t_gen = time.perf_counter() - t0
 ndims = [nd for nd, _ in cells]
-evidence_many(chains[:4], kmax=2, ndim=ndims[:4], device=local)      # warm-up (module load, workspace)
+evidence_many(chains[:32], kmax=2, ndim=ndims[:32], device=local, nstreams=a.nstreams)   # warm-up (module load, workspaces)
 times = []
 for _ in range(a.reps):
     t0 = time.perf_counter()
-    loge, var, ms = evidence_many(chains, kmax=2, ndim=ndims, device=local)
+    loge, var, ms = evidence_many(chains, kmax=2, ndim=ndims, device=local, nstreams=a.nstreams)
     times.append(time.perf_counter() - t0)
-out = {'kind': a.kind, 'n_gpus': world, 'cells': len(cells), 'rows': int(sum(n for _, n in cells)),
+out = {'kind': a.kind, 'n_gpus': world, 'nstreams': a.nstreams, 'cells': len(cells), 'rows': int(sum(n for _, n in cells)),
        'pairs': float(sum(float(n) ** 2 for _, n in cells)), 'wall_s_best': min(times), 'wall_s_all': times,
        'device_ms_sum': float(np.sum(ms)), 'synthetic_generation_s': t_gen,
        'cells_per_s': len(cells) / min(times)}
