@@ -43,6 +43,34 @@ def test_knn_bit_exact(ctx, n, d, k, cross):
     assert st['launches'] >= 4
 
 
+@pytest.mark.parametrize('d', [1, 2, 3, 16])
+def test_wide_tile_at_low_ndim(ctx, d):
+    """The wide query tile (TQ=4, two-row prefetch; the default for large inputs at ndim <= 16, forced here):
+    spot rows against an exhaustive numpy scan, every row against the exact FP64 kernel on a query shard."""
+    n = 400000
+    rng = np.random.default_rng(50 + d)
+    x = rng.normal(size=(n, d))
+    try:
+        for name, v in (('filter_tq', 4), ('filter_tr', 8), ('filter_packed', 1), ('filter_sync', 3)):
+            ctx.set_option(name, v)
+        dk, ix, st = ctx.knn(x, 4, identity=True)
+    finally:
+        for name in ('filter_tq', 'filter_tr', 'filter_packed', 'filter_sync'):
+            ctx.set_option(name, -1)
+    assert st['filter_tq'] == 4 and st['filter_mode'] == 3
+    assert np.all(np.diff(dk, axis=1) >= 0) and np.array_equal(ix[:, 0], np.arange(n))
+    for r in rng.choice(n, 40, replace=False):
+        d2 = O.sq_dist_sequential(x[r:r + 1], x)[0]
+        d2[r] = np.inf
+        nn = np.lexsort((np.arange(n), d2))[:3]
+        assert np.array_equal(ix[r, 1:], nn)
+        np.testing.assert_array_equal(dk[r, 1:], np.sqrt(d2[nn]))
+    lo, hi = 123456, 123456 + 3000
+    ek, ei, _ = ctx.knn(x, 4, identity=True, q_range=(lo, hi), exact_only=True)
+    np.testing.assert_array_equal(ix[lo:hi], ei)
+    np.testing.assert_array_equal(dk[lo:hi], ek)
+
+
 def test_knn_exact_rescan_path(ctx):
     """The exhaustive FP64 kernel (used for rows the FP32 filter cannot certify) on its own."""
     rng = np.random.default_rng(3)
