@@ -178,7 +178,7 @@ def run_reference_arm(args, rank, world):
     wl = make_workload(args.workload)
     n_full = len(wl['s1'])
     budget = 150.0 / max(1, args.steps + args.warmup)
-    n_s, expo = pick_cpu_sample(wl, min(25.0, budget), n_full)
+    n_s, expo = pick_cpu_sample(wl, min(25.0, budget, args.cpu_seconds if args.cpu_seconds > 0 else 25.0), n_full)
     for _ in range(args.warmup):
         cpu_port_once(wl, n_s)
     times = []
@@ -214,7 +214,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--cpu-seconds', type=float, default=20.0)
+    ap.add_argument('--cpu-seconds', type=float, default=20.0,
+                    help='target seconds of CPU work for the cpu_baseline sample / per step of the reference arm')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-API leg (long scaling runs only)')
     ap.add_argument('--allow-short-warmup', action='store_true',
                     help='do not raise --warmup to 3 (minutes-long steps of the cfg5 scaling run only)')
