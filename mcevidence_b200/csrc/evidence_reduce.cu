@@ -9,6 +9,7 @@
 // t = -inf and contribute exactly 0, as volume = 0 does at MCEvidence.py:1110.
 // Summation order is fixed (grid size depends only on the row count): results are
 // reproducible run to run.
+#include "../../include/mcevidence_b200.h"
 #include "common.cuh"
 #include <math_constants.h>
 
@@ -54,8 +55,10 @@ struct Lse {
     }
 };
 
-__device__ __forceinline__ void block_merge(Lse& v, double* sh /* [3 * RED_THREADS/32] */) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+constexpr int MAX_NK = MCE_MAX_NEIGHBOURS;   // kmax - 1 <= 16 outputs
+
+// warp-level merge (fixed shuffle tree: deterministic)
+__device__ __forceinline__ void warp_merge(Lse& v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const double om = __shfl_down_sync(0xffffffffu, v.m, o);
@@ -63,49 +66,61 @@ __device__ __forceinline__ void block_merge(Lse& v, double* sh /* [3 * RED_THREA
         const double o2 = __shfl_down_sync(0xffffffffu, v.s2, o);
         v.merge(om, o1, o2);
     }
-    __syncthreads();
-    if (lane == 0) { sh[warp * 3] = v.m; sh[warp * 3 + 1] = v.s1; sh[warp * 3 + 2] = v.s2; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < RED_THREADS / 32; ++w) v.merge(sh[w * 3], sh[w * 3 + 1], sh[w * 3 + 2]);
-    }
 }
 
+// One pass over the rows: logL_j - log w_j is evaluated once per row and shared by all k.
 __global__ void __launch_bounds__(RED_THREADS) partials_kernel(const ReduceParams p) {
-    __shared__ double sh[3 * RED_THREADS / 32];
+    __shared__ double sh[MAX_NK][RED_THREADS / 32][3];
     const long long nq = p.q_end - p.q_begin;
     const double dd = (double)p.d;
-    for (int k = 0; k < p.nk; ++k) {
-        Lse acc;
-        acc.init();
-        const int col = p.col0 + p.first_nb - 1 + k;
-        for (long long ql = (long long)blockIdx.x * RED_THREADS + threadIdx.x; ql < nq;
-             ql += (long long)gridDim.x * RED_THREADS) {
-            const long long row = p.q_begin + ql;
-            const double r = p.dknn[ql * p.ld + col];
-            const double t = dd * log(r) + p.logl[row] - log(p.weights[row]);
-            acc.add(t);
+    const int col0 = p.col0 + p.first_nb - 1;
+    Lse acc[MAX_NK];
+#pragma unroll
+    for (int k = 0; k < MAX_NK; ++k) acc[k].init();
+    for (long long ql = (long long)blockIdx.x * RED_THREADS + threadIdx.x; ql < nq;
+         ql += (long long)gridDim.x * RED_THREADS) {
+        const long long row = p.q_begin + ql;
+        const double base = p.logl[row] - log(p.weights[row]);
+        const double* r = p.dknn + ql * p.ld + col0;
+#pragma unroll
+        for (int k = 0; k < MAX_NK; ++k)
+            if (k < p.nk) acc[k].add(dd * log(r[k]) + base);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < MAX_NK; ++k) {
+        if (k < p.nk) {
+            warp_merge(acc[k]);
+            if (lane == 0) { sh[k][warp][0] = acc[k].m; sh[k][warp][1] = acc[k].s1; sh[k][warp][2] = acc[k].s2; }
         }
-        block_merge(acc, sh);
-        if (threadIdx.x == 0) {
-            double* o = p.block_partial + ((long long)blockIdx.x * p.nk + k) * 3;
-            o[0] = acc.m; o[1] = acc.s1; o[2] = acc.s2;
-        }
+    }
+    __syncthreads();
+    if (threadIdx.x < p.nk) {
+        const int k = threadIdx.x;
+        Lse v;
+        v.init();
+        for (int w = 0; w < RED_THREADS / 32; ++w) v.merge(sh[k][w][0], sh[k][w][1], sh[k][w][2]);
+        double* o = p.block_partial + ((long long)blockIdx.x * p.nk + k) * 3;
+        o[0] = v.m; o[1] = v.s1; o[2] = v.s2;
     }
 }
 
+// One warp per output k: lanes stride over the block partials, then a fixed shuffle tree.
 __global__ void final_kernel(const double* block_partial, int nblocks, int nk, double* out) {
-    const int k = threadIdx.x;
-    if (k >= nk) return;
+    const int k = blockIdx.x;
+    const int lane = threadIdx.x;
     Lse acc;
     acc.init();
-    for (int b = 0; b < nblocks; ++b) {
+    for (int b = lane; b < nblocks; b += 32) {
         const double* o = block_partial + ((long long)b * nk + k) * 3;
         acc.merge(o[0], o[1], o[2]);
     }
-    out[k * 3] = acc.m;
-    out[k * 3 + 1] = acc.s1;
-    out[k * 3 + 2] = acc.s2;
+    warp_merge(acc);
+    if (lane == 0) {
+        out[k * 3] = acc.m;
+        out[k * 3 + 1] = acc.s1;
+        out[k * 3 + 2] = acc.s2;
+    }
 }
 
 }  // namespace
@@ -119,7 +134,7 @@ int reduce_grid_size(long long nq) {
 
 void launch_reduce(const ReduceParams& p, int grid, cudaStream_t st, int* launches) {
     partials_kernel<<<grid, RED_THREADS, 0, st>>>(p);
-    final_kernel<<<1, 32, 0, st>>>(p.block_partial, grid, p.nk, p.out);
+    final_kernel<<<p.nk, 32, 0, st>>>(p.block_partial, grid, p.nk, p.out);
     *launches += 2;
 }
 
