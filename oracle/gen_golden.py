@@ -162,6 +162,16 @@ def main():
     c[:, 2:8] = c[:, 2:8] * scale + shift
     run_case(ref, 'auto_d6_scaled', [c], 108, kmax=3, priorvolume=1e-3)
 
+    # batch-size sweep (A7): first S rows per batch, covariance of ALL samples, SumW of all of s1
+    # (MCEvidence.py:808-840, 1034-1045, 1126); returns MLE[:, 1:] of shape (nbatch, kmax-1)
+    c, _ = gaussian_chain(2600, 5, seed=91, nextra=1)
+    run_case(ref, 'auto_d5_batches', [c], 110, kmax=3, ndim=5, nbatch=3, brange=[2.6, 3.4], bscale='logpower')
+
+    # covtype='single' in cross mode: s2 whitened with its own eigen-system, J of s1 (MCEvidence.py:1052-1054,
+    # 1080-1086) -- the two partitions live in different bases, so the explicit W / W_ref path is exercised
+    c, _ = gaussian_chain(3200, 5, seed=92, mean_shift=0.4)
+    run_case(ref, 'cross_d5_covsingle', [c], 111, kmax=3, split=True, evidence_kwargs={'covtype': 'single'})
+
 
 if __name__ == '__main__':
     main()

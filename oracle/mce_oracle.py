@@ -191,8 +191,15 @@ def evidence_from_dknn_log(dknn, logl, weight, ndim, kmax, k0, sum_w, log_jac, l
 # whole path                                          (MCEvidence.py:1033-1157)
 # --------------------------------------------------------------------------
 def evidence(s1, logl1, w1, ndim, kmax, s2=None, priorvolume=1.0, adjusted_weights=None,
-             knn='sklearn', n_jobs=-1, scalar_loop=False, return_parts=False):
-    """Restatement of ``MCEvidence.evidence()`` for one batch, covtype ``'all'``.
+             knn='sklearn', n_jobs=-1, scalar_loop=False, return_parts=False,
+             covtype='all', cov_from=None, sum_w=None):
+    """Restatement of ``MCEvidence.evidence()`` for one batch.
+
+    ``covtype='all'`` (the default of ``evidence()``): one covariance of s1 U s2, or of ``cov_from`` when
+    given -- in a batch-size sweep the covariance is that of ALL samples while s1 is a prefix
+    (MCEvidence.py:1034-1045, 860-861), and ``sum_w`` is then the weight sum of all of s1 (``:1126``).
+    ``covtype='single'``: s1 whitened with its own eigen-system, s2 (cross mode) with its own, J of s1
+    (``:1052-1054, 1080-1086``).
 
     ``s1`` (S, >=ndim) samples of partition s1, ``logl1 = -loglikes`` (the sign
     flip of ``arrays()``, MCEvidence.py:399), ``w1`` weights; ``s2`` the second
@@ -208,10 +215,15 @@ def evidence(s1, logl1, w1, ndim, kmax, s2=None, priorvolume=1.0, adjusted_weigh
         allsamp = np.concatenate((s1, s2))                      # :413, :860-861
     else:
         allsamp = s1
-    cs = covariance_stats(allsamp)                              # :1034-1037
+    if covtype == 'single':
+        cs = covariance_stats(s1)                               # :1052-1054
+        cs_ref = covariance_stats(s2) if cross else cs          # :1080-1081 (J stays that of s1)
+    else:
+        cs = covariance_stats(allsamp if cov_from is None else np.asarray(cov_from, dtype=np.float64)[:, :ndim])
+        cs_ref = cs                                             # :1034-1037
     y1 = whiten(s1, cs['eVec'], cs['eVal'])                     # :1057
     if cross:
-        y2 = whiten(s2, cs['eVec'], cs['eVal'])                 # :1086
+        y2 = whiten(s2, cs_ref['eVec'], cs_ref['eVal'])         # :1086
         ref, k0 = y2, 0                                         # :1093-1096
     else:
         ref, k0 = y1, 1                                         # :1099-1101
@@ -225,7 +237,8 @@ def evidence(s1, logl1, w1, ndim, kmax, s2=None, priorvolume=1.0, adjusted_weigh
             dknn = np.concatenate((np.zeros((len(y1), 1)), d), axis=1)
             idx = np.concatenate((np.arange(len(y1))[:, None], i), axis=1)
     aw = w1 if adjusted_weights is None else adjusted_weights
-    sum_w = np.sum(aw)                                          # :1126
+    if sum_w is None:
+        sum_w = np.sum(aw)                                      # :1126
     mle = evidence_from_dknn_linear(dknn, logl1, w1, ndim, kmax, k0, sum_w, cs['J'],
                                     math.log(priorvolume), scalar_loop=scalar_loop)
     if return_parts:

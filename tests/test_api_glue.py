@@ -20,7 +20,7 @@ def test_evidence_glue_matches_reference(golden, tmp_path, oracle_ctx):
     mce = M.MCEvidence(g.method(tmp_path), verbose=0, **g.ctor)
     assert mce.kmax == g.kmax and mce.ndim == g.ndim
     mle = mce.evidence(**g.ev)
-    assert mle.shape == g.mle.shape == (g.kmax - 1,)
+    assert mle.shape == g.mle.shape and mle.shape[-1] == g.kmax - 1
     assert np.abs(mle - g.mle).max() < 1e-9
     out, info = mce.evidence(info=True, **g.ev)
     assert set(info) == {'NparamsMC', 'Nsamples_read', 'Nparams_read', 'NparamsCosmo', 'Nsamples'}

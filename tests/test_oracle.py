@@ -43,9 +43,16 @@ def test_oracle_reproduces_reference(golden, knn):
     if g.ev.get('pos_lnp'):
         logl = -logl
     pv = g.ev.get('pvolume', g.ctor.get('priorvolume', 1.0))
+    if 'brange' in g.ctor:
+        # batch-size sweep: prefixes of s1, covariance and SumW of everything (MCEvidence.py:1034-1045, 1126)
+        sizes = [int(pow(10.0, x)) for x in np.linspace(min(g.ctor['brange']), max(g.ctor['brange']), g.ctor['nbatch'])]
+        rows = [O.evidence(s1.samples[:S], logl[:S], s1.weights[:S], g.ndim, g.ctor.get('kmax', 5), priorvolume=pv,
+                           knn=knn, cov_from=s1.samples, sum_w=np.sum(s1.weights)) for S in sizes]
+        assert np.abs(np.array(rows) - g.mle).max() <= (0.0 if knn == 'sklearn' else 1e-9)
+        return
     mle, parts = O.evidence(s1.samples, logl, s1.weights, g.ndim, g.ctor.get('kmax', 5),
                             s2=None if s2.samples is None else s2.samples, priorvolume=pv, knn=knn,
-                            return_parts=True)
+                            return_parts=True, covtype=g.ev.get('covtype', 'all'))
     assert mle.shape == g.mle.shape
     # the restatement follows the reference line by line: same summation order, same library calls
     tol = 0.0 if knn == 'sklearn' else 1e-9
