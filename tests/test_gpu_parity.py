@@ -298,7 +298,7 @@ def test_golden_reference_outputs(ctx, golden, tmp_path):
     err = np.abs(mle - g.mle).max()
     # the ill-conditioned case is limited by the reference's own eig() accuracy, not by this path
     assert err < (LOGE_TOL if g.name == 'auto_d6_scaled' else LOGE_TIGHT), err
-    assert mce.last_stats['launches'] >= 8
+    assert mce.last_stats['launches'] >= 6      # K1..K4 (+ K0 when the library estimates the covariance)
 
 
 def test_golden_knn_arrays(ctx):
