@@ -146,6 +146,14 @@ int  mce_combine_partials(int nparts, int nk, const double *parts, double *out);
 int  mce_finalize(const double *partials, int nk, int d, int cross, int64_t n_query_total, double log_sum_w,
                   double log_jacobian, double log_prior_volume, double *logE, double *var_logE);
 
+/* The work-decomposition model of the filter (host arithmetic, no device needed; for inspection and tests):
+   how many query blocks run as whole-set units (`nfull`) and into how many reference ranges the remaining
+   blocks are split (`chunks`) for a GPU with `sm_count` SMs holding `ctas_per_sm` CTAs of `queries_per_cta`
+   queries; `wide` selects the constants of the four-queries-per-thread tile.  `cost` (optional) is the
+   modelled time in comparable units. */
+int  mce_plan_split(int sm_count, int d, int64_t n_query, int64_t n_ref, int list_len, int queries_per_cta,
+                    int ctas_per_sm, int wide, int *nfull, int *chunks, double *cost);
+
 /* FP32 FMA microbenchmark on the context's device: variant 0 = scalar FFMA, 1 = packed FFMA2 (2-4: other
    FFMA2 operand-sharing patterns, see csrc/fma_peak.cu).
    Reports achieved TFLOP/s counting 2 FLOP per lane-FMA, the roofline denominator of the filter. */

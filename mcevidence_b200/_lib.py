@@ -97,6 +97,8 @@ def load_library():
         lib.mce_finalize.argtypes = [c_double_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_double,
                                      C.c_double, c_double_p, c_double_p]
         lib.mce_fma_peak.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p]
+        lib.mce_plan_split.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.POINTER(C.c_int), C.POINTER(C.c_int), c_double_p]
         lib.mce_read_chain_text.argtypes = [C.c_char_p, C.c_int, C.POINTER(c_double_p), c_int64_p, c_int64_p]
         lib.mce_free_host.argtypes = [C.c_void_p]
         lib.mce_free_host.restype = None
@@ -339,6 +341,16 @@ def finalize(partials, ndim, cross, n_query_total, log_sum_w, log_jacobian, log_
                                  float(log_prior_volume), loge.ctypes.data_as(c_double_p),
                                  var.ctypes.data_as(c_double_p)))
     return loge, var
+
+
+def plan_split(n_query, n_ref, ndim, list_len=5, queries_per_cta=256, ctas_per_sm=4, wide=False, sm_count=148):
+    """``mce_plan_split``: ``(nfull, chunks, cost)`` of the filter's work decomposition (host arithmetic)."""
+    lib = load_library()
+    nfull, chunks, cost = C.c_int(), C.c_int(), C.c_double()
+    _check(lib, lib.mce_plan_split(int(sm_count), int(ndim), int(n_query), int(n_ref), int(list_len),
+                                   int(queries_per_cta), int(ctas_per_sm), int(bool(wide)), C.byref(nfull),
+                                   C.byref(chunks), C.byref(cost)))
+    return nfull.value, chunks.value, cost.value
 
 
 def read_chain_text(path, nthreads=0):

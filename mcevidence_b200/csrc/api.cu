@@ -723,6 +723,22 @@ int mce_finalize(const double* partials, int nk, int d, int cross, int64_t n_que
     return MCE_OK;
 }
 
+int mce_plan_split(int sm_count, int d, int64_t n_query, int64_t n_ref, int list_len, int queries_per_cta,
+                   int ctas_per_sm, int wide, int* nfull, int* chunks, double* cost) {
+    if (sm_count < 1 || d < 1 || n_query < 1 || n_ref < 1 || list_len < 1 || queries_per_cta < 1 || ctas_per_sm < 1 ||
+        !nfull || !chunks)
+        return fail(MCE_ERR_ARG, "bad arguments to mce_plan_split");
+    const int TJ = tile_refs(d);
+    const int ntiles = (int)((n_ref + TJ - 1) / TJ);
+    const int max_chunks = ntiles / 4 > 1 ? (ntiles / 4 > 64 ? 64 : ntiles / 4) : 1;
+    const SplitPlan pl = plan_split((n_query + queries_per_cta - 1) / queries_per_cta, sm_count, queries_per_cta,
+                                    ctas_per_sm, n_ref, list_len, d, wide != 0, max_chunks);
+    *nfull = pl.nfull;
+    *chunks = pl.chunks;
+    if (cost) *cost = pl.cost;
+    return MCE_OK;
+}
+
 int mce_fma_peak(mce_ctx* c, int variant, int iters, double* tflops, double* ms_out) {
     if (!c || !tflops) return fail(MCE_ERR_ARG, "ctx or tflops is NULL");
     if (variant < 0 || variant > 4 || iters < 1) return fail(MCE_ERR_ARG, "bad variant/iters");

@@ -108,3 +108,27 @@ def test_missing_library_raises(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, 'LIB_PATH', str(tmp_path / 'nope.so'))
     with pytest.raises(ImportError, match='no CPU fallback'):
         _lib.load_library()
+
+
+def test_split_planner_invariants():
+    """mce_plan_split (host arithmetic of the filter's work decomposition): structural invariants."""
+    slots = 148 * 4
+    for n in (1, 300, 15000, 125000, 1000000, 16000000):
+        for d in (1, 7, 10, 27, 64):
+            for n_ref in (n, max(1, n // 3), 4 * n + 17):
+                nfull, chunks, cost = _lib.plan_split(n, n_ref, d)
+                nblocks = -(-n // 256)
+                assert 0 <= nfull <= nblocks and nfull % slots == 0        # whole waves only
+                assert 1 <= chunks <= 64 and cost > 0
+                if nfull == nblocks:
+                    assert chunks == 1
+    # large inputs: whole-set units for the full waves, a modest split of the remainder
+    nfull, chunks, _ = _lib.plan_split(1000000, 1000000, 10)
+    assert nfull == (3907 // slots) * slots and 2 <= chunks <= 16
+    # fewer blocks than CTA slots: split until every slot has a unit
+    nfull, chunks, _ = _lib.plan_split(15000, 15000, 10)
+    assert nfull == 0 and 59 * chunks >= slots * 0.9
+    # the insertion cost weighs more at low ndim: never more splits than at high ndim for the same shape
+    c_lo = _lib.plan_split(125000, 1000000, 2)[1]
+    c_hi = _lib.plan_split(125000, 1000000, 30)[1]
+    assert c_lo <= c_hi
