@@ -104,7 +104,7 @@ typedef struct mce_stats {
     int32_t filter_smem;
     int32_t filter_ctas_per_sm;
     float   rmax;            /* largest whitened reference norm (enters the error bound) */
-    int32_t filter_mode;     /* 0 free-running warps, 1 CTA barrier per tile group, 2+ with register prefetch */
+    int32_t filter_mode;     /* 0 free-running warps, 1 CTA barrier per tile group, 2+ with register prefetch; 16 = tcgen05 engine */
 } mce_stats;
 
 typedef struct mce_result {
@@ -127,8 +127,16 @@ void mce_ctx_destroy(mce_ctx *ctx);
    stream; pass cudaStreamLegacy ((void*)1) for the default stream.  NULL restores the context's own stream. */
 int  mce_ctx_set_stream(mce_ctx *ctx, void *cuda_stream);
 /* Tuning knobs: "filter_tq", "filter_tr", "filter_packed", "filter_sync" (kernel mode 0/1/2), "ref_chunks"
-   (uniform split of the reference set), "list_margin". -1 = automatic. */
+   (uniform split of the reference set), "list_margin". -1 = automatic.
+   "filter_engine": 0 = FP32 FFMA filter (default), 1 = tcgen05 tensor-core filter (TF32 coarse scores in TMEM,
+   exact FP32 evaluation of the columns that pass; same candidates contract, stats.filter_mode reports 16).
+   Diagnostics of engine 1: "tc_check" (1: also evaluate every pair exactly and record the worst
+   |coarse - exact| / allowance, read back with mce_ctx_get_debug), "tc_slack_percent" (scales the allowance,
+   default 100), "tc_swap_offsets" (exchange the two byte offsets of the shared-memory matrix descriptors). */
 int  mce_ctx_set_option(mce_ctx *ctx, const char *name, int value);
+/* Diagnostics of the last call on this context: "tc_check_ratio" (worst |coarse - exact| / allowance seen by a
+   "tc_check" run; must stay below 1), "tc_check_pairs" (pairs compared, modulo 2^32), "filter_engine". */
+int  mce_ctx_get_debug(mce_ctx *ctx, const char *name, double *value);
 
 int  mce_evidence(mce_ctx *ctx, const mce_problem *problem, mce_result *result);
 int  mce_evidence_batch(mce_ctx *ctx, int n, const mce_problem *problems, mce_result *results);

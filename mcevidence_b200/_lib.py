@@ -90,6 +90,7 @@ def load_library():
         lib.mce_ctx_destroy.restype = None
         lib.mce_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         lib.mce_ctx_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        lib.mce_ctx_get_debug.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double)]
         lib.mce_evidence.argtypes = [C.c_void_p, C.POINTER(Problem), C.POINTER(Result)]
         lib.mce_evidence_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(Problem), C.POINTER(Result)]
         lib.mce_knn.argtypes = [C.c_void_p, C.POINTER(Problem), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Stats)]
@@ -163,6 +164,12 @@ class Context:
 
     def set_option(self, name, value):
         _check(self._lib, self._lib.mce_ctx_set_option(self._h, name.encode(), int(value)))
+
+    def get_debug(self, name):
+        """``mce_ctx_get_debug``: diagnostics of the last call (e.g. ``tc_check_ratio``)."""
+        v = C.c_double(0.0)
+        _check(self._lib, self._lib.mce_ctx_get_debug(self._h, name.encode(), C.byref(v)))
+        return v.value
 
     # ------------------------------------------------------------------
     def _problem(self, query, ref, logl, weights, ndim, kmax, W, W_ref, mu, log_jacobian, log_sum_w,

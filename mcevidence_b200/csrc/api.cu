@@ -89,7 +89,12 @@ struct mce_ctx {
     cudaStream_t stream = nullptr;
     std::mutex mu;
     int opt_tq = -1, opt_tr = -1, opt_packed = -1, opt_chunks = -1, opt_margin = -1, opt_sync = -1, opt_tail = -1;
-    DevBuf xq, xr, logl, w, yr, yq, tiles, cand_idx, cand_th, dknn, idx, flagged, covpart, redpart, scal, sink, exact;
+    // tensor-core engine of the filter (opt-in): 0 = FFMA filter, 1 = tcgen05; check = also evaluate every pair
+    // exactly and record the worst |coarse - exact| / e; slack = percent of the default error allowance
+    int opt_engine = 0, opt_tc_check = 0, opt_tc_swap = 0, opt_tc_slack = 100;
+    double dbg_tc_ratio = 0.0, dbg_tc_pairs = 0.0;
+    DevBuf xq, xr, logl, w, yr, yq, tiles, tc_tiles, tc_debug, cand_idx, cand_th, dknn, idx, flagged, covpart, redpart, scal,
+        sink, exact;
     DevScalars* hscal = nullptr;  // pinned
     cudaEvent_t ev[EV_COUNT] = {};
 };
@@ -326,6 +331,12 @@ int run_problem(mce_ctx* c, const Run& r) {
                       &launches);
         yq_base = c->yr.as<double>();
     }
+    const bool use_tc = c->opt_engine == 1 && !(p.flags & MCE_FLAG_EXACT_ONLY);
+    if (use_tc) {
+        rc = c->tc_tiles.ensure(tc_image_bytes(n_ref, d));
+        if (rc) return rc;
+        launch_tc_image(c->yr.as<double>(), c->tiles.as<float>(), n_ref, d, c->tc_tiles.as<float>(), st, &launches);
+    }
     CU(cudaEventRecord(c->ev[EV_WHITEN], st));
 
     // ---- K2: FP32 filter ---------------------------------------------------------------------
@@ -338,9 +349,15 @@ int run_problem(mce_ctx* c, const Run& r) {
     if (c->opt_tr > 0) cfg.tr = c->opt_tr;
     if (c->opt_packed >= 0) cfg.packed = c->opt_packed;
     if (c->opt_sync >= 0) cfg.sync = c->opt_sync;
-    int qpc = 0, smem = 0, ctas = 0;
-    const int max_chunks = ntiles / 4 > 1 ? (ntiles / 4 > 64 ? 64 : ntiles / 4) : 1;
-    if (c->opt_tq <= 0 && c->opt_tr <= 0 && c->opt_packed < 0 && c->opt_sync < 0 && d <= 16) {
+    int qpc = 0, smem = 0, ctas = 0, tc_stages = 0;
+    // tiles of the engine in use: the split of the reference set is made at tile boundaries
+    const int ftiles = use_tc ? (int)((n_ref + TC_TILE_REFS - 1) / TC_TILE_REFS) : ntiles;
+    const int max_chunks = ftiles / 4 > 1 ? (ftiles / 4 > 64 ? 64 : ftiles / 4) : 1;
+    if (use_tc) {
+        if (tc_filter_query(d, list_len, &qpc, &smem, &ctas, &tc_stages) != 0)
+            return fail(MCE_ERR_ARG, "no tensor-core filter for ndim=%d list_len=%d", d, list_len);
+        cfg = FilterConfig{1, TC_TILE_REFS, 0, 16};   // reported in the stats: mode 16 = tcgen05 engine
+    } else if (c->opt_tq <= 0 && c->opt_tr <= 0 && c->opt_packed < 0 && c->opt_sync < 0 && d <= 16) {
         // Low ndim: four queries per thread (half the shared-memory traffic per FMA, two-row prefetch) is
         // 2-11 % faster when its 512-query blocks fill the GPU; the modelled cost decides (small inputs
         // fill the GPU with fewer reference splits using the 256-query blocks of the default).
@@ -356,7 +373,7 @@ int run_problem(mce_ctx* c, const Run& r) {
             cudaGetLastError();
         }
     }
-    if (filter_query(d, cfg, list_len, &qpc, &smem, &ctas) != 0) {
+    if (!use_tc && filter_query(d, cfg, list_len, &qpc, &smem, &ctas) != 0) {
         cudaGetLastError();
         FilterConfig def;
         filter_default_config(d, list_len, &def);
@@ -382,9 +399,9 @@ int run_problem(mce_ctx* c, const Run& r) {
         chunks = pl.chunks;
         nfull = pl.nfull;
     }
-    if (chunks > ntiles) chunks = ntiles;
-    const int tiles_per_chunk = (ntiles + chunks - 1) / chunks;
-    chunks = (ntiles + tiles_per_chunk - 1) / tiles_per_chunk;
+    if (chunks > ftiles) chunks = ftiles;
+    const int tiles_per_chunk = (ftiles + chunks - 1) / chunks;
+    chunks = (ftiles + tiles_per_chunk - 1) / tiles_per_chunk;
     if (chunks == 1) nfull = nqblocks;
 
     // candidate planes: chunk 0 for every query, chunks 1.. only for the queries of the split blocks
@@ -412,15 +429,37 @@ int run_problem(mce_ctx* c, const Run& r) {
         fp.tail_q0 = tail_q0;
         fp.self_offset = 0;
         fp.self_exclude = cross ? 0 : 1;
-        fp.ntiles = ntiles;
+        fp.ntiles = ftiles;
         fp.tiles_per_chunk = tiles_per_chunk;
         fp.ref_chunks = chunks;
         fp.nqblocks = nqblocks;
         fp.nfull = nfull;
         fp.list_len = list_len;
         fp.d = d;
-        if (launch_filter(fp, cfg, st, &launches) != 0)
+        if (use_tc) {
+            // Bound on |coarse - exact| per pair, e = slack_qr |q| Rmax + slack_rr Rmax^2: both operands are
+            // truncated to TF32 (2^-10 relative each, 2^-9 (1 + 2^-10) on a product, summed with Cauchy-Schwarz),
+            // h = h_hi + h_lo loses at most 2^-20 |h|, and 2^-14 (|q| |r| + |h|) is allowed for the accumulation
+            // inside the tensor core (FP32 would need K 2^-24); 1.25 on top.
+            rc = c->tc_debug.ensure(2 * sizeof(unsigned int));
+            if (rc) return rc;
+            CU(cudaMemsetAsync(c->tc_debug.p, 0, 2 * sizeof(unsigned int), st));
+            const double scale = 1.25 * (double)c->opt_tc_slack / 100.0;
+            TcFilterParams tp;
+            tp.f = fp;
+            tp.f.tiles = c->tc_tiles.as<float>();
+            tp.rmax_bits = &ds->rmax_bits;
+            tp.slack_qr = (float)(scale * (ldexp(1.0, -9) * (1.0 + ldexp(1.0, -10)) + ldexp(1.0, -14)));
+            tp.slack_rr = (float)(scale * 0.5 * (ldexp(1.0, -20) + ldexp(1.0, -14)));
+            tp.debug = c->tc_debug.as<unsigned int>();
+            tp.stages = tc_stages;
+            tp.swap_offsets = c->opt_tc_swap;
+            tp.check = c->opt_tc_check;
+            if (launch_tc_filter(tp, st, &launches) != 0)
+                return fail(MCE_ERR_CUDA, "tensor-core filter launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        } else if (launch_filter(fp, cfg, st, &launches) != 0) {
             return fail(MCE_ERR_CUDA, "filter launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
     }
     CU(cudaEventRecord(c->ev[EV_FILTER], st));
 
@@ -513,6 +552,14 @@ int run_problem(mce_ctx* c, const Run& r) {
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
 
+    if (use_tc && c->opt_tc_check && !exact_only) {
+        unsigned int dbg[2] = {0, 0};
+        CU(cudaMemcpy(dbg, c->tc_debug.p, sizeof(dbg), cudaMemcpyDeviceToHost));
+        float ratio;
+        memcpy(&ratio, &dbg[0], 4);
+        c->dbg_tc_ratio = ratio;
+        c->dbg_tc_pairs = dbg[1];
+    }
     if (c->hscal->status != 0)
         return fail(MCE_ERR_NOT_POSDEF,
                     "sample covariance of the %d selected parameters is not positive definite "
@@ -621,7 +668,7 @@ void mce_ctx_destroy(mce_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
-    DevBuf* bufs[] = {&c->xq, &c->xr, &c->logl, &c->w, &c->yr, &c->yq, &c->tiles, &c->cand_idx, &c->cand_th,
+    DevBuf* bufs[] = {&c->xq, &c->xr, &c->logl, &c->w, &c->yr, &c->yq, &c->tiles, &c->tc_tiles, &c->tc_debug, &c->cand_idx, &c->cand_th,
                       &c->dknn, &c->idx, &c->flagged, &c->covpart, &c->redpart, &c->scal, &c->sink, &c->exact};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; ++i)
@@ -648,7 +695,26 @@ int mce_ctx_set_option(mce_ctx* c, const char* name, int value) {
     else if (!strcmp(name, "list_margin")) c->opt_margin = value;
     else if (!strcmp(name, "filter_sync")) c->opt_sync = value;
     else if (!strcmp(name, "tail_chunks")) c->opt_tail = value;
+    else if (!strcmp(name, "filter_engine")) {
+        if (value != 0 && value != 1) return fail(MCE_ERR_ARG, "filter_engine must be 0 (FFMA) or 1 (tcgen05)");
+        c->opt_engine = value;
+    } else if (!strcmp(name, "tc_check")) c->opt_tc_check = value != 0;
+    else if (!strcmp(name, "tc_swap_offsets")) c->opt_tc_swap = value != 0;
+    else if (!strcmp(name, "tc_slack_percent")) {
+        if (value < 1) return fail(MCE_ERR_ARG, "tc_slack_percent must be positive");
+        c->opt_tc_slack = value;
+    }
     else return fail(MCE_ERR_ARG, "unknown option '%s'", name);
+    return MCE_OK;
+}
+
+int mce_ctx_get_debug(mce_ctx* c, const char* name, double* value) {
+    if (!c || !name || !value) return fail(MCE_ERR_ARG, "ctx, name or value is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!strcmp(name, "tc_check_ratio")) *value = c->dbg_tc_ratio;
+    else if (!strcmp(name, "tc_check_pairs")) *value = c->dbg_tc_pairs;
+    else if (!strcmp(name, "filter_engine")) *value = c->opt_engine;
+    else return fail(MCE_ERR_ARG, "unknown debug value '%s'", name);
     return MCE_OK;
 }
 

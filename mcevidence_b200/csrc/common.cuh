@@ -97,6 +97,31 @@ int filter_query(int d, const FilterConfig& cfg, int list_len, int* queries_per_
 int launch_filter(const FilterParams& p, const FilterConfig& cfg, cudaStream_t st, int* launches);
 void filter_default_config(int d, int list_len, FilterConfig* cfg);
 
+// ---- K2 (tensor-core engine, opt-in): tcgen05 TF32 coarse scores + exact FP32 slow path -------
+// Same unit decomposition, candidate planes and threshold semantics as the FFMA filter, so K3 is
+// shared.  Reference image: tiles of TC_TILE_REFS rows, each K-major in the UMMA "interleaved"
+// (no-swizzle) canonical layout [K/4 chunks][16 row groups][8 rows][4 floats]; column d and d+1 of
+// a row hold h split into a TF32-exact head and the remainder, the other padding columns are 0.
+constexpr int TC_TILE_REFS = 128;     // reference rows per tile (UMMA N)
+constexpr int TC_QUERIES = 256;       // queries per CTA: two UMMA M=128 blocks
+__host__ __device__ constexpr int tc_kpad(int d) { return (d + 2 + 7) / 8 * 8; }   // K: coordinates + (h_hi, h_lo), multiple of 8
+struct TcFilterParams {
+    FilterParams f;                   // f.tiles = TC image; f.ntiles / f.tiles_per_chunk count TC tiles
+    const unsigned int* rmax_bits;    // max |y| over the references (written by K1)
+    float slack_qr, slack_rr;         // coarse-score error bound e = slack_qr |q| Rmax + slack_rr Rmax^2
+    unsigned int* debug;              // CHECK builds: [0] max over pairs of |coarse - exact| / e as float bits, [1] pairs checked (mod 2^32)
+    int stages;                       // shared-memory ring depth
+    int swap_offsets;                 // debug: exchange the leading/stride byte offsets of the descriptors
+    int check;                        // 1: evaluate every pair exactly as well and record the worst ratio in debug[]
+};
+size_t tc_image_bytes(long long n_ref, int d);
+// Builds the TC image from the whitened FP64 rows and the h row of the FFMA tiles (bitwise the same h).
+void launch_tc_image(const double* y64, const float* ffma_tiles, long long n_ref, int d, float* image, cudaStream_t st,
+                     int* launches);
+// Returns 0 and fills the launch shape on success, -1 if the configuration cannot run.
+int tc_filter_query(int d, int list_len, int* queries_per_cta, int* smem_bytes, int* ctas_per_sm, int* stages);
+int launch_tc_filter(const TcFilterParams& p, cudaStream_t st, int* launches);
+
 // ---- K3: FP64 re-rank + verification, exact re-scan ---------------------------------------
 struct RerankParams {
     const double* yq;        // whitened queries

@@ -1,0 +1,562 @@
+// K2-TC: tensor-core engine of the neighbour filter (tcgen05 + TMEM + TMA, sm_100a).  Opt-in
+// ("filter_engine" = 1); the FFMA filter of knn_filter.cuh stays the default until this engine has
+// been validated on hardware.
+//
+// Replaces the same reference step as the FFMA filter, the neighbour search of
+// NearestNeighbors.kneighbors (MCEvidence.py:1104), and writes the same candidate planes, so the
+// FP64 re-rank / verification (K3) is shared.
+//
+// One CTA = one (query block of 256, reference range) unit, 10 warps:
+//   warps 0-7  epilogue: warp w owns TMEM lane quadrant w%4 of query block w/4; thread = one query
+//   warp  8    TMA producer: one bulk copy per 128-reference tile into a shared-memory ring
+//   warp  9    MMA issuer: per tile 2 x K/8 tcgen05.mma.kind::tf32 (M=128 queries x N=128
+//              references) into one of two TMEM accumulator buffers, then tcgen05.commit
+// A row = [q_0..q_{d-1}, 1, 1, 0..], B row = [r_0..r_{d-1}, h_hi, h_lo, 0..] with h = -|r|^2/2, so
+// the accumulator holds the ranking score s = q.r - |r|^2/2 of the FFMA filter, evaluated with
+// TF32-truncated operands ("coarse").  Both operand tiles keep the full FP32 words; the tensor
+// core ignores the low 13 mantissa bits.
+//
+// Selection.  The epilogue reads 32 accumulator columns per tcgen05.ld, takes their maximum
+// (FMNMX3 tree, about half an ALU instruction per pair) and compares it with th - e, where th is
+// the query's current threshold (minimum of its top-L list) and e bounds |coarse - exact| for
+// every reference (operand truncation 2^-10 each, h split into a TF32-exact head and a remainder,
+// generous allowance for the accumulation inside the tensor core).  Only columns that pass are
+// evaluated exactly: the FP32 FMA chain of the FFMA filter, read from the very same operand tiles,
+// and inserted if they beat th.  Hence no reference whose FP32 score exceeds the final threshold
+// is ever dropped, which is the invariant K3's verification relies on.
+#include "common.cuh"
+#include "knn_filter.cuh"
+#include <math_constants.h>
+
+namespace mce {
+
+namespace {
+
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_PRODUCER_WARP = 8;
+constexpr int TC_MMA_WARP = 9;
+constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
+constexpr int TC_QBLK = 128;                 // UMMA M
+constexpr uint32_t TC_TMEM_COLS = 512;       // 2 accumulator buffers x 2 query blocks x 128 columns
+constexpr uint32_t TC_CHUNK_BYTES = (TC_TILE_REFS / 8) * 128;   // one 16-byte K chunk of all rows of a tile: 2048
+constexpr uint32_t TC_ROWGROUP_BYTES = 128;                     // one 8-row core matrix
+constexpr int TC_CHUNK_FLOATS = TC_CHUNK_BYTES / 4;             // 512
+constexpr int TC_SMEM_BUDGET = 200 * 1024;
+// instruction descriptor (kind::tf32): D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2), both K-major
+// (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_TILE_REFS >> 3) << 17) |
+                              ((uint32_t)(TC_QBLK >> 4) << 24);
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// shared-memory matrix descriptor, K-major, no swizzle: 8 rows x 16 bytes core matrices; `lbo` = byte distance
+// between core matrices adjacent in K, `sbo` = between core matrices adjacent in M/N; bit 46 = sm_100 version
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+// D[tmem] (+)= A[smem] . B[smem]^T, issued by one thread for the CTA
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 32 lanes x 32 consecutive columns: register i of lane l <- TMEM[lane0 + l][col0 + i]
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+// Wait for this thread's outstanding tcgen05.ld.  The registers are listed as read-write operands so that no
+// use of them can be scheduled above the wait.
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                   "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                   "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
+
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+// maximum of 32 scores: 17 FMNMX(3) in three levels
+__device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
+    float a[11];
+#pragma unroll
+    for (int j = 0; j < 10; ++j)
+        a[j] = max3(__uint_as_float(v[3 * j]), __uint_as_float(v[3 * j + 1]), __uint_as_float(v[3 * j + 2]));
+    a[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+    const float b0 = max3(a[0], a[1], a[2]), b1 = max3(a[3], a[4], a[5]), b2 = max3(a[6], a[7], a[8]);
+    const float b3 = fmaxf(a[9], a[10]);
+    return fmaxf(max3(b0, b1, b2), b3);
+}
+
+// Replace the minimum of the list of one query (entries strided by TC_QUERIES); the caller guarantees
+// s > current minimum.  Returns the new minimum = new threshold.
+__device__ __forceinline__ float tc_list_insert(float* ls, int* li, int len, float s, int idx) {
+    float m = ls[0];
+    int am = 0;
+    float second = CUDART_INF_F;
+    for (int e = 1; e < len; ++e) {
+        const float v = ls[e * TC_QUERIES];
+        if (v < m) {
+            second = m;
+            m = v;
+            am = e;
+        } else if (v < second) {
+            second = v;
+        }
+    }
+    ls[am * TC_QUERIES] = s;
+    li[am * TC_QUERIES] = idx;
+    return fminf(s, second);
+}
+
+// Exact FP32 score from the FP32 words of the operand tiles: the FMA chain of the FFMA filter
+// (accumulator initialised with h, coordinates in order).  Element k of a row sits at
+// [(k >> 2) * TC_CHUNK_FLOATS + (k & 3)] from the row's first 16-byte chunk.
+__device__ __forceinline__ float tc_exact_score(const float* __restrict__ arow, const float* __restrict__ bcol, int d) {
+    const float h = bcol[(d >> 2) * TC_CHUNK_FLOATS + (d & 3)] + bcol[((d + 1) >> 2) * TC_CHUNK_FLOATS + ((d + 1) & 3)];
+    float acc = fmaf(arow[0], bcol[0], h);
+    for (int c = 1; c < d; ++c) {
+        const int o = (c >> 2) * TC_CHUNK_FLOATS + (c & 3);
+        acc = fmaf(arow[o], bcol[o], acc);
+    }
+    return acc;
+}
+
+// Slow path for one column that passed the coarse test.
+__device__ __noinline__ float tc_consider(const float* arow, const float* bcol, int d, float th, float* ls, int* li,
+                                          int len, int ridx, int self) {
+    const float s = tc_exact_score(arow, bcol, d);
+    if (s > th && ridx != self) th = tc_list_insert(ls, li, len, s, ridx);
+    return th;
+}
+
+struct TcEpiState {
+    const float* arow;   // this query's row in the A tile
+    float* ls;
+    int* li;
+    float th, tcut, e_q;
+    float worst;         // CHECK: max |coarse - exact| / e over the pairs of this thread
+    unsigned int checked;
+    uint32_t full_bar, full_parity;   // "TMA bytes landed" barrier of the tile being processed
+    int d, len, self;
+};
+
+// The epilogue learns about a tile through the accumulator barrier only; before it reads the operand tile
+// itself it observes the tile's own TMA barrier (already complete, so this never spins).
+__device__ __forceinline__ void tc_acquire_tile(const TcEpiState& st) {
+    while (!mbar_try_wait(st.full_bar, st.full_parity)) {
+    }
+}
+
+// one group of 32 columns [col0, col0 + 32) of the tile at `tile`
+template <bool CHECK>
+__device__ __forceinline__ void tc_process(const uint32_t (&v)[32], int col0, const float* tile, int ridx0, TcEpiState& st) {
+    if constexpr (CHECK) {
+        if (st.th < CUDART_INF_F) {   // valid query
+            tc_acquire_tile(st);
+#pragma unroll 1
+            for (int i = 0; i < 32; ++i) {
+                float coarse = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j == i) coarse = __uint_as_float(v[j]);
+                const int col = col0 + i;
+                const float ex = tc_exact_score(st.arow, tile + (col >> 3) * 32 + (col & 7) * 4, st.d);
+                if (ex > -CUDART_INF_F && st.e_q > 0.f) {
+                    st.worst = fmaxf(st.worst, fabsf(coarse - ex) / st.e_q);
+                    st.checked++;
+                }
+            }
+        }
+    }
+    const float m = max32(v);
+    if (m > st.tcut) {
+        tc_acquire_tile(st);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            if (__uint_as_float(v[i]) > st.tcut) {
+                const int col = col0 + i;
+                st.th = tc_consider(st.arow, tile + (col >> 3) * 32 + (col & 7) * 4, st.d, st.th, st.ls, st.li, st.len,
+                                    ridx0 + col, st.self);
+                st.tcut = st.th - st.e_q;
+            }
+        }
+    }
+}
+
+template <int KSTEPS, bool CHECK>
+__global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFilterParams tp) {
+    constexpr int K = KSTEPS * 8;
+    constexpr uint32_t TILE_BYTES = (uint32_t)K * TC_TILE_REFS * 4;   // K/4 chunks of 2 KB
+    constexpr int TILE_FLOATS = K * TC_TILE_REFS;
+    constexpr uint32_t A_MB_BYTES = (uint32_t)K * TC_QBLK * 4;
+    constexpr uint32_t KSTEP_BYTES = 2 * TC_CHUNK_BYTES;              // one MMA consumes K = 8 TF32 = two chunks
+    const FilterParams& p = tp.f;
+    const int NS = tp.stages;
+    const int L = p.list_len;
+
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float* a_sm = reinterpret_cast<float*>(smem_raw);
+    float* ring = reinterpret_cast<float*>(smem_raw + 2 * A_MB_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * A_MB_BYTES + (size_t)NS * TILE_BYTES);
+    uint64_t* bar_full = bars;              // [NS]  TMA bytes of a tile have landed
+    uint64_t* bar_free = bars + NS;         // [NS]  all epilogue warps are done with the tile in the slot
+    uint64_t* bar_acc_full = bars + 2 * NS; // [2]   the MMAs of a tile have completed
+    uint64_t* bar_acc_free = bars + 2 * NS + 2;   // [2] all epilogue warps have read the accumulator buffer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 4);
+    float* ls = reinterpret_cast<float*>(tmem_slot + 4);
+    int* li = reinterpret_cast<int*>(ls + (size_t)L * TC_QUERIES);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    if (*p.status != 0) return;   // the whitening matrix is garbage: the host reports the error
+
+    // unit -> (query block, reference chunk), as in the FFMA filter
+    int qblock, rchunk, t0, t1;
+    if ((int)blockIdx.x < p.nfull) {
+        qblock = blockIdx.x;
+        rchunk = 0;
+        t0 = 0;
+        t1 = p.ntiles;
+    } else {
+        const int v = blockIdx.x - p.nfull;
+        const int rem = p.nqblocks - p.nfull;
+        rchunk = v / rem;
+        qblock = p.nfull + v % rem;
+        t0 = rchunk * p.tiles_per_chunk;
+        t1 = min(t0 + p.tiles_per_chunk, p.ntiles);
+    }
+    const int nt = t1 - t0;
+    const long long nq = p.q_end - p.q_begin;
+
+    // ---- set-up ----------------------------------------------------------------------------------
+    if (warp == TC_MMA_WARP) tmem_alloc(smem_u32(tmem_slot), TC_TMEM_COLS);
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(smem_u32(&bar_full[s]), 1);
+            mbar_init(smem_u32(&bar_free[s]), TC_EPI_WARPS);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(smem_u32(&bar_acc_full[b]), 1);
+            mbar_init(smem_u32(&bar_acc_free[b]), TC_EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    TcEpiState st;
+    st.worst = 0.f;
+    st.checked = 0;
+    const long long ql = (long long)qblock * TC_QUERIES + tid;   // epilogue threads: local query id
+    if (warp < TC_EPI_WARPS) {
+        const int mb = tid >> 7, row = tid & 127;
+        const bool valid = ql < nq;
+        const double* src = p.yq + (p.q_begin + (valid ? ql : 0)) * p.d;
+        float* arow = a_sm + mb * (K * TC_QBLK) + (row >> 3) * 32 + (row & 7) * 4;
+        float qn2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < K / 4; ++c) {
+            float w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int k = 4 * c + i;
+                float x = 0.f;
+                if (valid) {
+                    if (k < p.d) {
+                        x = (float)src[k];
+                        qn2 = fmaf(x, x, qn2);
+                    } else if (k < p.d + 2) {
+                        x = 1.f;
+                    }
+                }
+                w[i] = x;
+            }
+            *reinterpret_cast<float4*>(arow + c * TC_CHUNK_FLOATS) = make_float4(w[0], w[1], w[2], w[3]);
+        }
+        const float rmax = __uint_as_float(*tp.rmax_bits);
+        const float qn = sqrtf(qn2) * 1.000001f;
+        st.arow = arow;
+        st.ls = ls + tid;
+        st.li = li + tid;
+        st.e_q = tp.slack_qr * qn * rmax + tp.slack_rr * rmax * rmax;
+        st.th = valid ? -CUDART_INF_F : CUDART_INF_F;
+        st.tcut = st.th;
+        st.d = p.d;
+        st.len = L;
+        st.self = p.self_exclude ? (int)(p.q_begin + ql + p.self_offset) : -0x7fffffff;
+        for (int e = 0; e < L; ++e) {
+            st.ls[e * TC_QUERIES] = -CUDART_INF_F;
+            st.li[e * TC_QUERIES] = -1;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // A tile: generic-proxy stores -> tensor-core reads
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // ---- roles ------------------------------------------------------------------------------------
+    if (warp == TC_PRODUCER_WARP) {
+        if (lane == 0) {
+            const unsigned char* gt = reinterpret_cast<const unsigned char*>(p.tiles) + (size_t)t0 * TILE_BYTES;
+            int slot = 0, round = 0;
+            for (int n = 0; n < nt; ++n) {
+                if (round > 0) {
+                    const uint32_t fb = smem_u32(&bar_free[slot]);
+                    while (!mbar_try_wait(fb, (uint32_t)(round - 1) & 1u)) {
+                    }
+                }
+                const uint32_t bar = smem_u32(&bar_full[slot]);
+                mbar_arrive_expect_tx(bar, TILE_BYTES);
+                tma_bulk_g2s(smem_u32(ring) + (uint32_t)slot * TILE_BYTES, gt + (size_t)n * TILE_BYTES, TILE_BYTES, bar);
+                if (++slot == NS) {
+                    slot = 0;
+                    ++round;
+                }
+            }
+        }
+    } else if (warp == TC_MMA_WARP) {
+        const uint32_t a_base = smem_u32(a_sm), ring_base = smem_u32(ring);
+        const uint32_t lbo = tp.swap_offsets ? TC_ROWGROUP_BYTES : TC_CHUNK_BYTES;
+        const uint32_t sbo = tp.swap_offsets ? TC_CHUNK_BYTES : TC_ROWGROUP_BYTES;
+        int slot = 0, round = 0;
+        for (int it = 0; it < nt; ++it) {
+            const int buf = it & 1;
+            {
+                const uint32_t fb = smem_u32(&bar_full[slot]);
+                while (!mbar_try_wait(fb, (uint32_t)round & 1u)) {
+                }
+            }
+            if (it >= 2) {
+                const uint32_t ab = smem_u32(&bar_acc_free[buf]);
+                while (!mbar_try_wait(ab, (uint32_t)((it >> 1) - 1) & 1u)) {
+                }
+            }
+            tc_fence_after();
+            if (lane == 0) {
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u + (uint32_t)mb * 128u;
+#pragma unroll
+                    for (int ks = 0; ks < KSTEPS; ++ks) {
+                        const uint64_t adesc = tc_smem_desc(a_base + mb * A_MB_BYTES + ks * KSTEP_BYTES, lbo, sbo);
+                        const uint64_t bdesc = tc_smem_desc(ring_base + (uint32_t)slot * TILE_BYTES + ks * KSTEP_BYTES, lbo, sbo);
+                        umma_tf32(d_tmem, adesc, bdesc, TC_IDESC, ks > 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit(smem_u32(&bar_acc_full[buf]));
+            }
+            __syncwarp();
+            if (++slot == NS) {
+                slot = 0;
+                ++round;
+            }
+        }
+    } else {
+        const int mb = warp >> 2, quad = warp & 3;
+        const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)mb * 128u;
+        int slot = 0, round = 0;
+        for (int it = 0; it < nt; ++it) {
+            const int buf = it & 1;
+            {
+                const uint32_t fb = smem_u32(&bar_acc_full[buf]);
+                while (!mbar_try_wait(fb, (uint32_t)(it >> 1) & 1u)) {
+                }
+            }
+            tc_fence_after();
+            st.full_bar = smem_u32(&bar_full[slot]);
+            st.full_parity = (uint32_t)round & 1u;
+            const uint32_t taddr = tlane + (uint32_t)buf * 256u;
+            const float* tile = ring + (size_t)slot * TILE_FLOATS;
+            const int ridx0 = (t0 + it) * TC_TILE_REFS;
+            uint32_t va[32], vb[32];
+            tmem_ld32(taddr, va);
+            tmem_wait_ld(va);
+            tmem_ld32(taddr + 32, vb);
+            tc_process<CHECK>(va, 0, tile, ridx0, st);
+            tmem_wait_ld(vb);
+            tmem_ld32(taddr + 64, va);
+            tc_process<CHECK>(vb, 32, tile, ridx0, st);
+            tmem_wait_ld(va);
+            tmem_ld32(taddr + 96, vb);
+            tc_process<CHECK>(va, 64, tile, ridx0, st);
+            tmem_wait_ld(vb);
+            // the accumulator buffer has been read by this warp: hand it back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_acc_free[buf]));
+            tc_process<CHECK>(vb, 96, tile, ridx0, st);
+            // the slow path reads the operand tile: release the ring slot only now
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_free[slot]));
+            if (++slot == NS) {
+                slot = 0;
+                ++round;
+            }
+        }
+        if (ql < nq) {
+            p.cand_th[cand_th_offset(rchunk, ql, p.nq_pad, p.ntail_pad, p.tail_q0)] = st.th;
+            for (int e = 0; e < L; ++e)
+                p.cand_idx[cand_idx_offset(rchunk, e, ql, L, p.nq_pad, p.ntail_pad, p.tail_q0)] = st.li[e * TC_QUERIES];
+        }
+        if constexpr (CHECK) {
+            if (tp.debug) {
+                atomicMax(&tp.debug[0], __float_as_uint(st.worst));   // non-negative floats order like their bits
+                atomicAdd(&tp.debug[1], st.checked);
+            }
+        }
+    }
+
+    // ---- tear-down -------------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    }
+}
+
+size_t tc_fixed_smem(int K, int list_len) {
+    return (size_t)2 * K * TC_QBLK * 4 + (size_t)(2 * 8 + 4) * sizeof(uint64_t) + 16 +
+           (size_t)list_len * TC_QUERIES * (sizeof(float) + sizeof(int));
+}
+
+template <int KSTEPS>
+int tc_launch_k(const TcFilterParams& tp, unsigned grid, size_t smem, cudaStream_t st) {
+    if (tp.check) {
+        auto kern = knn_filter_tc_kernel<KSTEPS, true>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        kern<<<grid, TC_THREADS, smem, st>>>(tp);
+    } else {
+        auto kern = knn_filter_tc_kernel<KSTEPS, false>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        kern<<<grid, TC_THREADS, smem, st>>>(tp);
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// reference image: one thread per reference row
+__global__ void __launch_bounds__(128) tc_image_kernel(const double* __restrict__ y64, const float* __restrict__ ffma_tiles,
+                                                        long long n_ref, long long n_pad, int d, int K,
+                                                        float* __restrict__ image) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_pad) return;
+    const bool valid = j < n_ref;
+    const int TJ = tile_refs(d);
+    float h_hi = -CUDART_INF_F, h_lo = 0.f;
+    if (valid) {
+        const float h = ffma_tiles[(j / TJ) * (long long)((d + 1) * TJ) + (j % TJ)];   // row 0 of the FFMA tile
+        h_hi = __uint_as_float(__float_as_uint(h) & 0xFFFFE000u);                       // exact in TF32
+        h_lo = h - h_hi;                                                                 // exact in FP32
+        if (!(fabsf(h) < CUDART_INF_F)) {
+            h_hi = h;
+            h_lo = 0.f;
+        }
+    }
+    const long long tile = j / TC_TILE_REFS;
+    const int col = (int)(j - tile * TC_TILE_REFS);
+    float* dst = image + tile * (long long)(K * TC_TILE_REFS) + (col >> 3) * 32 + (col & 7) * 4;
+    const double* src = y64 + (valid ? j : 0) * d;
+    for (int c = 0; c < K / 4; ++c) {
+        float w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = 4 * c + i;
+            float x = 0.f;
+            if (k < d) x = valid ? (float)src[k] : 0.f;
+            else if (k == d) x = h_hi;
+            else if (k == d + 1) x = h_lo;
+            w[i] = x;
+        }
+        *reinterpret_cast<float4*>(dst + (long long)c * TC_CHUNK_FLOATS) = make_float4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+}  // namespace
+
+size_t tc_image_bytes(long long n_ref, int d) {
+    const long long ntiles = (n_ref + TC_TILE_REFS - 1) / TC_TILE_REFS;
+    return (size_t)ntiles * tc_kpad(d) * TC_TILE_REFS * sizeof(float);
+}
+
+void launch_tc_image(const double* y64, const float* ffma_tiles, long long n_ref, int d, float* image, cudaStream_t st,
+                     int* launches) {
+    const long long n_pad = (n_ref + TC_TILE_REFS - 1) / TC_TILE_REFS * TC_TILE_REFS;
+    if (n_pad == 0) return;
+    tc_image_kernel<<<(unsigned)((n_pad + 127) / 128), 128, 0, st>>>(y64, ffma_tiles, n_ref, n_pad, d, tc_kpad(d), image);
+    *launches += 1;
+}
+
+int tc_filter_query(int d, int list_len, int* queries_per_cta, int* smem_bytes, int* ctas_per_sm, int* stages) {
+    if (d < 1 || d > MAX_DIM) return -1;
+    const int K = tc_kpad(d);
+    const size_t tile = (size_t)K * TC_TILE_REFS * 4;
+    const size_t fixed = tc_fixed_smem(K, list_len);
+    if (fixed + 2 * tile > 227 * 1024) return -1;
+    long long ns = ((long long)TC_SMEM_BUDGET - (long long)fixed) / (long long)tile;
+    if (ns > 8) ns = 8;
+    if (ns < 2) ns = 2;
+    *queries_per_cta = TC_QUERIES;
+    *smem_bytes = (int)(fixed + (size_t)ns * tile);
+    *ctas_per_sm = 1;   // a CTA owns all 512 TMEM columns
+    *stages = (int)ns;
+    return 0;
+}
+
+int launch_tc_filter(const TcFilterParams& tp, cudaStream_t st, int* launches) {
+    const FilterParams& p = tp.f;
+    const int K = tc_kpad(p.d);
+    const size_t smem = tc_fixed_smem(K, p.list_len) + (size_t)tp.stages * K * TC_TILE_REFS * 4;
+    const unsigned grid = (unsigned)p.nfull + (unsigned)(p.nqblocks - p.nfull) * (unsigned)p.ref_chunks;
+    int rc = -1;
+    switch (K / 8) {
+        case 1: rc = tc_launch_k<1>(tp, grid, smem, st); break;
+        case 2: rc = tc_launch_k<2>(tp, grid, smem, st); break;
+        case 3: rc = tc_launch_k<3>(tp, grid, smem, st); break;
+        case 4: rc = tc_launch_k<4>(tp, grid, smem, st); break;
+        case 5: rc = tc_launch_k<5>(tp, grid, smem, st); break;
+        case 6: rc = tc_launch_k<6>(tp, grid, smem, st); break;
+        case 7: rc = tc_launch_k<7>(tp, grid, smem, st); break;
+        case 8: rc = tc_launch_k<8>(tp, grid, smem, st); break;
+        case 9: rc = tc_launch_k<9>(tp, grid, smem, st); break;
+        default: break;
+    }
+    if (rc == 0) *launches += 1;
+    return rc;
+}
+
+}  // namespace mce

@@ -1,0 +1,130 @@
+"""Bring-up of the tcgen05 filter engine on a B200 (``filter_engine`` = 1), safest case first.
+
+    gpurun --timeout 900 -- 'python tools/tc_bringup.py'
+
+Every stage runs in its own process under a timeout, so a kernel that spins on a barrier costs one stage, not
+the GPU call.  Stages:
+  1  tiny    300 x 3, tc_check: neighbours vs the FP64 oracle, worst |coarse - exact| / allowance
+  1s the same with the two descriptor byte offsets exchanged (only if stage 1 returns wrong neighbours)
+  2  shapes  one case per K padding (ndim 5, 10, 20, 27, 40, 64), auto and cross, split reference set
+  3  speed   cfg2 shard / full (N = 1e6, ndim 10) and ndim 27: ms_filter of both engines, identical neighbours
+Results: gpurun_out/tc_bringup.json (one record per stage) and the log on stdout.
+"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, 'gpurun_out')
+
+STAGE_CODE = r'''
+import json, sys, time
+import numpy as np
+sys.path.insert(0, %(root)r)
+from mcevidence_b200 import _lib as L
+from oracle import mce_oracle as O
+
+def oracle_knn(x, k, ref=None):
+    if ref is not None:
+        return O.knn_brute_fp64(ref, x, k)
+    d, i = O.knn_brute_fp64(x, x, k - 1, exclude_self=True)
+    return (np.concatenate((np.zeros((len(x), 1)), d), axis=1),
+            np.concatenate((np.arange(len(x))[:, None], i), axis=1))
+
+stage = %(stage)r
+ctx = L.default_context(0)
+ctx.set_option('filter_engine', 1)
+rec = {'stage': stage}
+if stage in ('1', '1s'):
+    ctx.set_option('tc_swap_offsets', 1 if stage == '1s' else 0)
+    ctx.set_option('tc_check', 1)
+    rng = np.random.default_rng(1)
+    x = rng.normal(size=(300, 3))
+    dk, ix, st = ctx.knn(x, 3, identity=True)
+    od, oi = oracle_knn(x, 3)
+    rec.update(idx_equal=bool(np.array_equal(ix, oi)), dist_equal=bool(np.array_equal(dk, od)),
+               wrong_rows=int((ix != oi).any(axis=1).sum()), ratio=ctx.get_debug('tc_check_ratio'),
+               pairs=ctx.get_debug('tc_check_pairs'), rescanned=int(st['rows_rescanned']), mode=int(st['filter_mode']))
+elif stage == '2':
+    ctx.set_option('tc_check', 1)
+    cases = []
+    for (n, d, k, cross, chunks) in [(2000, 5, 5, False, -1), (3000, 10, 5, False, -1), (3000, 10, 9, True, 3),
+                                     (2500, 20, 4, False, -1), (2000, 27, 5, True, -1), (1000, 40, 3, False, 2),
+                                     (1500, 64, 2, False, -1), (20000, 8, 3, False, -1)]:
+        rng = np.random.default_rng(1000 * d + n)
+        x = rng.normal(size=(n, d)) * (1 + rng.random(d)) + rng.normal(size=d)
+        ref = rng.normal(size=(n + 37, d)) * (1 + rng.random(d)) if cross else None
+        ctx.set_option('ref_chunks', chunks)
+        dk, ix, st = ctx.knn(x, k, ref=ref, identity=True)
+        od, oi = oracle_knn(x, k, ref)
+        cases.append(dict(n=n, d=d, k=k, cross=cross, chunks=chunks, idx_equal=bool(np.array_equal(ix, oi)),
+                          dist_equal=bool(np.array_equal(dk, od)), ratio=ctx.get_debug('tc_check_ratio'),
+                          rescanned=int(st['rows_rescanned']), ms_filter=st['ms_filter']))
+        print(cases[-1], flush=True)
+    rec['cases'] = cases
+elif stage == '3':
+    from mcevidence_b200.synthetic import gaussian_chain
+    runs = []
+    for (n, d, qn) in [(1000000, 10, 125000), (1000000, 10, 0), (1000000, 27, 125000), (400000, 5, 0), (1000000, 20, 125000)]:
+        chain, _ = gaussian_chain(n, d, seed=0)
+        x = np.ascontiguousarray(chain[:, 2:])
+        q_range = (0, qn) if qn else None
+        out = {}
+        for eng in (0, 1):
+            ctx.set_option('filter_engine', eng)
+            best = None
+            for rep in range(3):
+                dk, ix, st = ctx.knn(x, 5, q_range=q_range)
+                if best is None or st['ms_filter'] < best['ms_filter']:
+                    best = st
+            out[eng] = (dk, ix, best)
+        same = bool(np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][0], out[1][0]))
+        runs.append(dict(n=n, d=d, queries=qn or n, ms_filter_ffma=out[0][2]['ms_filter'], ms_filter_tc=out[1][2]['ms_filter'],
+                         same_neighbours=same, rescanned_tc=int(out[1][2]['rows_rescanned']),
+                         grid_tc=int(out[1][2]['filter_grid']), chunks_tc=int(out[1][2]['ref_chunks']),
+                         smem_tc=int(out[1][2]['filter_smem'])))
+        print(runs[-1], flush=True)
+    rec['runs'] = runs
+print('RECORD ' + json.dumps(rec), flush=True)
+'''
+
+
+def run_stage(stage, timeout):
+    code = STAGE_CODE % {'root': ROOT, 'stage': stage}
+    try:
+        r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    except subprocess.TimeoutExpired as e:
+        print('stage %s: TIMEOUT after %ds' % (stage, timeout))
+        print((e.stdout or b'').decode() if isinstance(e.stdout, bytes) else (e.stdout or ''))
+        return {'stage': stage, 'timeout': True}
+    sys.stdout.write(r.stdout)
+    if r.returncode != 0:
+        sys.stdout.write(r.stderr[-3000:])
+        return {'stage': stage, 'returncode': r.returncode, 'stderr': r.stderr[-1500:]}
+    for line in r.stdout.splitlines():
+        if line.startswith('RECORD '):
+            return json.loads(line[7:])
+    return {'stage': stage, 'no_record': True}
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    recs = []
+    r1 = run_stage('1', 120)
+    recs.append(r1)
+    ok = r1.get('idx_equal') and r1.get('dist_equal')
+    if not ok and not r1.get('timeout'):
+        r1s = run_stage('1s', 120)
+        recs.append(r1s)
+        ok = False   # a layout fix is needed before going on
+    if ok:
+        recs.append(run_stage('2', 300))
+        recs.append(run_stage('3', 600))
+    with open(os.path.join(OUT, 'tc_bringup.json'), 'w') as fh:
+        json.dump(recs, fh, indent=1)
+    print(json.dumps(recs)[:4000])
+
+
+if __name__ == '__main__':
+    main()
