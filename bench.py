@@ -205,6 +205,18 @@ def run_reference_arm(args, rank, world):
 
 
 # ---------------------------------------------------------------------------------------------
+def _measured_tf32_peak():
+    """TF32 dense peak for the roofline of the tcgen05 engine: half of the measured bf16 figure of
+    MEASURED_PEAKS.json (tcgen05 issues K = 8 TF32 against K = 16 bf16 per instruction), else half of the
+    profiling guide's nominal 2250 TFLOP/s."""
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
+            bf16 = float(json.load(fh)['bf16_tflops'])
+        return bf16 / 2.0, 'MEASURED_PEAKS.json bf16_tflops / 2 (TF32 MMA has half the K per instruction)'
+    except Exception:
+        return 1125.0, 'nominal 2250 TFLOP/s bf16 / 2 (MEASURED_PEAKS.json not found)'
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -212,6 +224,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
+    ap.add_argument('--filter-engine', default='ffma', choices=['ffma', 'tc'],
+                    help="K2 engine: 'ffma' (default, FP32 FMA pipe) or 'tc' (opt-in tcgen05 engine, see DESIGN.md K2-TC)")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-seconds', type=float, default=20.0,
                     help='target seconds of CPU work for the cpu_baseline sample / per step of the reference arm')
@@ -245,6 +259,7 @@ def main():
     ctx = _lib.default_context(local_rank)
     stream = torch.cuda.current_stream(device)
     ctx.set_stream(stream.cuda_stream)
+    ctx.set_option('filter_engine', 1 if args.filter_engine == 'tc' else 0)
 
     wl = make_workload(args.workload) if rank == 0 else None
     meta = [None]
@@ -370,6 +385,16 @@ def main():
                     'fma_pipe_frac': (2.0 * d * pairs_launch / t_k2 / 1e12) / fma_peak,
                     'note': 'the filter issues d FMAs per pair (2d executed FLOP) for the 3d algorithmic FLOP of the '
                             'difference form, so frac can exceed 1; fma_pipe_frac is executed FMA rate / measured FMA peak'}
+        if stats['filter_mode'] == 16:
+            # tcgen05 engine: the d FMAs per pair run on the tensor cores as a TF32 MMA of depth K = 8 ceil((d+2)/8)
+            kpad = 8 * ((d + 2 + 7) // 8)
+            tf32_peak = _measured_tf32_peak()
+            mma = 2.0 * kpad * pairs_launch / t_k2 / 1e12
+            roofline.update({'bound': 'tensor', 'achieved': mma, 'peak': tf32_peak[0], 'frac': mma / tf32_peak[0],
+                             'kernel': 'knn_filter_tc_kernel<KSTEPS=%d>' % (kpad // 8), 'peak_source': tf32_peak[1],
+                             'algorithmic_tflops': achieved, 'fma_pipe_frac': None, 'frac_theoretical': None, 'traffic': None,
+                             'note': 'achieved = executed TF32 MMA FLOP (2 K per pair, K = %d for ndim %d); the algorithmic 3d '
+                                     'FLOP per pair are in algorithmic_tflops' % (kpad, d)})
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': t_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
                 'dtype': 'f32 filter, f64 re-rank/reduce', 'data': 'synthetic',
