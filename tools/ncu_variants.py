@@ -22,7 +22,7 @@ ap.add_argument('--chunks', type=int, default=-1)
 ap.add_argument('--reps', type=int, default=1)
 ap.add_argument('--qn', type=int, default=0, help='search only the first qn query rows (a rank shard)')
 ap.add_argument('--tail', type=int, nargs='*', default=[-1])
-ap.add_argument('--cfg', nargs='+', default=['2,8,1'])
+ap.add_argument('--cfg', nargs='+', default=['2,8,1'], help="tq,tr,packed[,mode] | auto | tc (tcgen05 engine)")
 a = ap.parse_args()
 chain, _ = gaussian_chain(a.n, a.d, seed=0)
 s, l, w = np.ascontiguousarray(chain[:, 2:]), -chain[:, 1], chain[:, 0]
@@ -30,7 +30,8 @@ ctx = _lib.Context(0)
 ctx.set_option('ref_chunks', a.chunks)
 for c, tail in [(c, t) for c in a.cfg for t in a.tail]:
     ctx.set_option('tail_chunks', tail)
-    parts = [-1, -1, -1, -1] if c == 'auto' else [int(x) for x in c.split(',')]
+    ctx.set_option('filter_engine', 1 if c == 'tc' else 0)
+    parts = [-1, -1, -1, -1] if c in ('auto', 'tc') else [int(x) for x in c.split(',')]
     tq, tr, pk = parts[:3]
     sy = parts[3] if len(parts) > 3 else -1
     ctx.set_option('filter_tq', tq); ctx.set_option('filter_tr', tr); ctx.set_option('filter_packed', pk)
