@@ -106,6 +106,19 @@ __device__ __forceinline__ void tmem_wait_ld(uint32_t (&v)[32]) {
                  : "memory");
 }
 
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ float max3(float a, float b, float c) {
     float r;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -331,7 +344,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
 
     // ---- roles ------------------------------------------------------------------------------------
     if (warp == TC_PRODUCER_WARP) {
-        if (lane == 0) {
+        if (elect_one()) {
             const unsigned char* gt = reinterpret_cast<const unsigned char*>(p.tiles) + (size_t)t0 * TILE_BYTES;
             int slot = 0, round = 0;
             for (int n = 0; n < nt; ++n) {
@@ -367,7 +380,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
                 }
             }
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
 #pragma unroll
                 for (int mb = 0; mb < 2; ++mb) {
                     const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u + (uint32_t)mb * 128u;
