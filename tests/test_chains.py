@@ -3,7 +3,6 @@ import numpy as np
 import pytest
 
 from mcevidence_b200.chains import MCSamples, read_chain_file
-from conftest import Golden
 
 
 def make(method, **kw):

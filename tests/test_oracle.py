@@ -5,7 +5,6 @@ import numpy as np
 import pytest
 
 from oracle import mce_oracle as O
-from conftest import Golden
 
 
 def partitions(g):

@@ -8,7 +8,6 @@ auto-mode evidence problem (kmax=2), batched chain-per-GPU.  Chains are syntheti
 """
 import argparse
 import json
-import math
 import os
 import sys
 import time
@@ -17,7 +16,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from mcevidence_b200 import _lib                       # noqa: E402
 from mcevidence_b200.grid import evidence_many         # noqa: E402
 from mcevidence_b200.synthetic import gaussian_chain   # noqa: E402
 
