@@ -125,16 +125,18 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
     return r;
 }
 
-// maximum of 32 scores: 17 FMNMX(3) in three levels
-__device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
+// maxima of 32 scores in three levels of FMNMX(3), 17 instructions: b[j] covers columns 9j .. 9j+8 (b[3]: 27..31)
+__device__ __forceinline__ float max32(const uint32_t (&v)[32], float (&b)[4]) {
     float a[11];
 #pragma unroll
     for (int j = 0; j < 10; ++j)
         a[j] = max3(__uint_as_float(v[3 * j]), __uint_as_float(v[3 * j + 1]), __uint_as_float(v[3 * j + 2]));
     a[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
-    const float b0 = max3(a[0], a[1], a[2]), b1 = max3(a[3], a[4], a[5]), b2 = max3(a[6], a[7], a[8]);
-    const float b3 = fmaxf(a[9], a[10]);
-    return fmaxf(max3(b0, b1, b2), b3);
+    b[0] = max3(a[0], a[1], a[2]);
+    b[1] = max3(a[3], a[4], a[5]);
+    b[2] = max3(a[6], a[7], a[8]);
+    b[3] = fmaxf(a[9], a[10]);
+    return fmaxf(max3(b[0], b[1], b[2]), b[3]);
 }
 
 // Replace the minimum of the list of one query (entries strided by TC_QUERIES); the caller guarantees
@@ -218,16 +220,23 @@ __device__ __forceinline__ void tc_process(const uint32_t (&v)[32], int col0, co
             }
         }
     }
-    const float m = max32(v);
+    float b[4];
+    const float m = max32(v, b);
     if (m > st.tcut) {
         tc_acquire_tile(st);
+        // only the sub-blocks whose maximum passed are scanned (th only rises, so a stale maximum is conservative)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            if (__uint_as_float(v[i]) > st.tcut) {
-                const int col = col0 + i;
-                st.th = tc_consider(st.arow, tile + (col >> 3) * 32 + (col & 7) * 4, st.d, st.th, st.ls, st.li, st.len,
-                                    ridx0 + col, st.self);
-                st.tcut = st.th - st.e_q;
+        for (int j = 0; j < 4; ++j) {
+            if (b[j] > st.tcut) {
+#pragma unroll
+                for (int i = 9 * j; i < (j == 3 ? 32 : 9 * j + 9); ++i) {
+                    if (__uint_as_float(v[i]) > st.tcut) {
+                        const int col = col0 + i;
+                        st.th = tc_consider(st.arow, tile + (col >> 3) * 32 + (col & 7) * 4, st.d, st.th, st.ls, st.li,
+                                            st.len, ridx0 + col, st.self);
+                        st.tcut = st.th - st.e_q;
+                    }
+                }
             }
         }
     }
