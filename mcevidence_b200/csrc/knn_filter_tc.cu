@@ -229,8 +229,9 @@ __device__ __forceinline__ void tc_process(const uint32_t (&v)[32], int col0, co
         for (int j = 0; j < 4; ++j) {
             if (b[j] > st.tcut) {
 #pragma unroll
-                for (int i = 9 * j; i < (j == 3 ? 32 : 9 * j + 9); ++i) {
-                    if (__uint_as_float(v[i]) > st.tcut) {
+                for (int ii = 0; ii < 9; ++ii) {
+                    const int i = 9 * j + ii;
+                    if (i < 32 && __uint_as_float(v[i < 32 ? i : 31]) > st.tcut) {
                         const int col = col0 + i;
                         st.th = tc_consider(st.arow, tile + (col >> 3) * 32 + (col & 7) * 4, st.d, st.th, st.ls, st.li,
                                             st.len, ridx0 + col, st.self);
