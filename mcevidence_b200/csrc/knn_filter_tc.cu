@@ -139,14 +139,26 @@ __device__ __forceinline__ float max32(const uint32_t (&v)[32], float (&b)[4]) {
     return fmaxf(max3(b[0], b[1], b[2]), b[3]);
 }
 
-// Replace the minimum of the list of one query (entries strided by TC_QUERIES); the caller guarantees
-// s > current minimum.  Returns the new minimum = new threshold.
-__device__ __forceinline__ float tc_list_insert(float* ls, int* li, int len, float s, int idx) {
-    float m = ls[0];
+// The slow path addresses shared memory explicitly (32-bit shared-window addresses): it sits behind a call,
+// where generic pointers would compile to generic loads.
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_s32(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+constexpr uint32_t TC_LIST_STRIDE = TC_QUERIES * 4;   // bytes between consecutive entries of one query's list
+
+// Replace the minimum of the list of one query; the caller guarantees s > current minimum.  Returns the
+// new minimum = new threshold.
+__device__ __forceinline__ float tc_list_insert(uint32_t ls, uint32_t li, int len, float s, int idx) {
+    float m = lds_f32(ls);
     int am = 0;
     float second = CUDART_INF_F;
     for (int e = 1; e < len; ++e) {
-        const float v = ls[e * TC_QUERIES];
+        const float v = lds_f32(ls + e * TC_LIST_STRIDE);
         if (v < m) {
             second = m;
             m = v;
@@ -155,36 +167,36 @@ __device__ __forceinline__ float tc_list_insert(float* ls, int* li, int len, flo
             second = v;
         }
     }
-    ls[am * TC_QUERIES] = s;
-    li[am * TC_QUERIES] = idx;
+    sts_f32(ls + am * TC_LIST_STRIDE, s);
+    sts_s32(li + am * TC_LIST_STRIDE, idx);
     return fminf(s, second);
 }
 
 // Exact FP32 score from the FP32 words of the operand tiles: the FMA chain of the FFMA filter
-// (accumulator initialised with h, coordinates in order).  Element k of a row sits at
-// [(k >> 2) * TC_CHUNK_FLOATS + (k & 3)] from the row's first 16-byte chunk.
-__device__ __forceinline__ float tc_exact_score(const float* __restrict__ arow, const float* __restrict__ bcol, int d) {
-    const float h = bcol[(d >> 2) * TC_CHUNK_FLOATS + (d & 3)] + bcol[((d + 1) >> 2) * TC_CHUNK_FLOATS + ((d + 1) & 3)];
-    float acc = fmaf(arow[0], bcol[0], h);
+// (accumulator initialised with h, coordinates in order).  Element k of a row sits
+// (k >> 2) * TC_CHUNK_BYTES + (k & 3) * 4 bytes after the row's first 16-byte chunk.
+__device__ __forceinline__ float tc_exact_score(uint32_t arow, uint32_t bcol, int d) {
+    const float h = lds_f32(bcol + (d >> 2) * TC_CHUNK_BYTES + (d & 3) * 4) +
+                    lds_f32(bcol + ((d + 1) >> 2) * TC_CHUNK_BYTES + ((d + 1) & 3) * 4);
+    float acc = fmaf(lds_f32(arow), lds_f32(bcol), h);
     for (int c = 1; c < d; ++c) {
-        const int o = (c >> 2) * TC_CHUNK_FLOATS + (c & 3);
-        acc = fmaf(arow[o], bcol[o], acc);
+        const uint32_t o = (c >> 2) * TC_CHUNK_BYTES + (c & 3) * 4;
+        acc = fmaf(lds_f32(arow + o), lds_f32(bcol + o), acc);
     }
     return acc;
 }
 
 // Slow path for one column that passed the coarse test.
-__device__ __noinline__ float tc_consider(const float* arow, const float* bcol, int d, float th, float* ls, int* li,
-                                          int len, int ridx, int self) {
+__device__ __noinline__ float tc_consider(uint32_t arow, uint32_t bcol, int d, float th, uint32_t ls, uint32_t li, int len,
+                                          int ridx, int self) {
     const float s = tc_exact_score(arow, bcol, d);
     if (s > th && ridx != self) th = tc_list_insert(ls, li, len, s, ridx);
     return th;
 }
 
 struct TcEpiState {
-    const float* arow;   // this query's row in the A tile
-    float* ls;
-    int* li;
+    uint32_t arow;       // shared address of this query's row in the A tile
+    uint32_t ls, li;     // shared addresses of entry 0 of this query's list (scores, indices)
     float th, tcut, e_q;
     float worst;         // CHECK: max |coarse - exact| / e over the pairs of this thread
     unsigned int checked;
@@ -201,7 +213,7 @@ __device__ __forceinline__ void tc_acquire_tile(const TcEpiState& st) {
 
 // one group of 32 columns [col0, col0 + 32) of the tile at `tile`
 template <bool CHECK>
-__device__ __forceinline__ void tc_process(const uint32_t (&v)[32], int col0, const float* tile, int ridx0, TcEpiState& st) {
+__device__ __forceinline__ void tc_process(const uint32_t (&v)[32], int col0, uint32_t tile, int ridx0, TcEpiState& st) {
     if constexpr (CHECK) {
         if (st.th < CUDART_INF_F) {   // valid query
             tc_acquire_tile(st);
@@ -212,7 +224,7 @@ __device__ __forceinline__ void tc_process(const uint32_t (&v)[32], int col0, co
                 for (int j = 0; j < 32; ++j)
                     if (j == i) coarse = __uint_as_float(v[j]);
                 const int col = col0 + i;
-                const float ex = tc_exact_score(st.arow, tile + (col >> 3) * 32 + (col & 7) * 4, st.d);
+                const float ex = tc_exact_score(st.arow, tile + (col >> 3) * TC_ROWGROUP_BYTES + (col & 7) * 16, st.d);
                 if (ex > -CUDART_INF_F && st.e_q > 0.f) {
                     st.worst = fmaxf(st.worst, fabsf(coarse - ex) / st.e_q);
                     st.checked++;
@@ -233,8 +245,8 @@ __device__ __forceinline__ void tc_process(const uint32_t (&v)[32], int col0, co
                     const int i = 9 * j + ii;
                     if (i < 32 && __uint_as_float(v[i < 32 ? i : 31]) > st.tcut) {
                         const int col = col0 + i;
-                        st.th = tc_consider(st.arow, tile + (col >> 3) * 32 + (col & 7) * 4, st.d, st.th, st.ls, st.li,
-                                            st.len, ridx0 + col, st.self);
+                        st.th = tc_consider(st.arow, tile + (col >> 3) * TC_ROWGROUP_BYTES + (col & 7) * 16, st.d, st.th,
+                                            st.ls, st.li, st.len, ridx0 + col, st.self);
                         st.tcut = st.th - st.e_q;
                     }
                 }
@@ -247,7 +259,6 @@ template <int KSTEPS, bool CHECK>
 __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFilterParams tp) {
     constexpr int K = KSTEPS * 8;
     constexpr uint32_t TILE_BYTES = (uint32_t)K * TC_TILE_REFS * 4;   // K/4 chunks of 2 KB
-    constexpr int TILE_FLOATS = K * TC_TILE_REFS;
     constexpr uint32_t A_MB_BYTES = (uint32_t)K * TC_QBLK * 4;
     constexpr uint32_t KSTEP_BYTES = 2 * TC_CHUNK_BYTES;              // one MMA consumes K = 8 TF32 = two chunks
     const FilterParams& p = tp.f;
@@ -332,9 +343,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
         }
         const float rmax = __uint_as_float(*tp.rmax_bits);
         const float qn = sqrtf(qn2) * 1.000001f;
-        st.arow = arow;
-        st.ls = ls + tid;
-        st.li = li + tid;
+        st.arow = smem_u32(arow);
+        st.ls = smem_u32(ls + tid);
+        st.li = smem_u32(li + tid);
         st.e_q = tp.slack_qr * qn * rmax + tp.slack_rr * rmax * rmax;
         st.th = valid ? -CUDART_INF_F : CUDART_INF_F;
         st.tcut = st.th;
@@ -342,8 +353,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
         st.len = L;
         st.self = p.self_exclude ? (int)(p.q_begin + ql + p.self_offset) : -0x7fffffff;
         for (int e = 0; e < L; ++e) {
-            st.ls[e * TC_QUERIES] = -CUDART_INF_F;
-            st.li[e * TC_QUERIES] = -1;
+            ls[e * TC_QUERIES + tid] = -CUDART_INF_F;
+            li[e * TC_QUERIES + tid] = -1;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // A tile: generic-proxy stores -> tensor-core reads
     }
@@ -424,19 +435,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
             st.full_bar = smem_u32(&bar_full[slot]);
             st.full_parity = (uint32_t)round & 1u;
             const uint32_t taddr = tlane + (uint32_t)buf * 256u;
-            const float* tile = ring + (size_t)slot * TILE_FLOATS;
+            const uint32_t tile = smem_u32(ring) + (uint32_t)slot * TILE_BYTES;
             const int ridx0 = (t0 + it) * TC_TILE_REFS;
+            // tcgen05.ld is warp-collective: the warp is re-converged after every (divergent) slow path
             uint32_t va[32], vb[32];
             tmem_ld32(taddr, va);
             tmem_wait_ld(va);
             tmem_ld32(taddr + 32, vb);
             tc_process<CHECK>(va, 0, tile, ridx0, st);
+            __syncwarp();
             tmem_wait_ld(vb);
             tmem_ld32(taddr + 64, va);
             tc_process<CHECK>(vb, 32, tile, ridx0, st);
+            __syncwarp();
             tmem_wait_ld(va);
             tmem_ld32(taddr + 96, vb);
             tc_process<CHECK>(va, 64, tile, ridx0, st);
+            __syncwarp();
             tmem_wait_ld(vb);
             // the accumulator buffer has been read by this warp: hand it back to the MMA issuer
             tc_fence_before();
@@ -454,7 +469,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
         if (ql < nq) {
             p.cand_th[cand_th_offset(rchunk, ql, p.nq_pad, p.ntail_pad, p.tail_q0)] = st.th;
             for (int e = 0; e < L; ++e)
-                p.cand_idx[cand_idx_offset(rchunk, e, ql, L, p.nq_pad, p.ntail_pad, p.tail_q0)] = st.li[e * TC_QUERIES];
+                p.cand_idx[cand_idx_offset(rchunk, e, ql, L, p.nq_pad, p.ntail_pad, p.tail_q0)] = li[e * TC_QUERIES + tid];
         }
         if constexpr (CHECK) {
             if (tp.debug) {
