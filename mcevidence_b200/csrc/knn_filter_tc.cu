@@ -431,6 +431,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
                 while (!mbar_try_wait(fb, (uint32_t)(it >> 1) & 1u)) {
                 }
             }
+            __syncwarp();   // lanes may leave the spin loop at different times
             tc_fence_after();
             st.full_bar = smem_u32(&bar_full[slot]);
             st.full_parity = (uint32_t)round & 1u;
