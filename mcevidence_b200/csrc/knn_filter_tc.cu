@@ -10,7 +10,7 @@
 //   warps 0-7  epilogue: warp w owns TMEM lane quadrant w%4 of query block w/4; thread = one query
 //   warp  8    TMA producer: one bulk copy per 128-reference tile into a shared-memory ring
 //   warp  9    MMA issuer: per tile 2 x K/8 tcgen05.mma.kind::tf32 (M=128 queries x N=128
-//              references) into one of two TMEM accumulator buffers, then tcgen05.commit
+//              references) into one of two TMEM accumulator buffers, one tcgen05.commit per query block
 // A row = [q_0..q_{d-1}, 1, 1, 0..], B row = [r_0..r_{d-1}, h_hi, h_lo, 0..] with h = -|r|^2/2, so
 // the accumulator holds the ranking score s = q.r - |r|^2/2 of the FFMA filter, evaluated with
 // TF32-truncated operands ("coarse").  Both operand tiles keep the full FP32 words; the tensor
@@ -271,9 +271,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * A_MB_BYTES + (size_t)NS * TILE_BYTES);
     uint64_t* bar_full = bars;              // [NS]  TMA bytes of a tile have landed
     uint64_t* bar_free = bars + NS;         // [NS]  all epilogue warps are done with the tile in the slot
-    uint64_t* bar_acc_full = bars + 2 * NS; // [2]   the MMAs of a tile have completed
-    uint64_t* bar_acc_free = bars + 2 * NS + 2;   // [2] all epilogue warps have read the accumulator buffer
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 4);
+    uint64_t* bar_acc_full = bars + 2 * NS; // [2 buffers][2 query blocks]  the MMAs of a tile for a query block have completed
+    uint64_t* bar_acc_free = bars + 2 * NS + 4;   // [2] all epilogue warps have read the accumulator buffer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 6);
     float* ls = reinterpret_cast<float*>(tmem_slot + 4);
     int* li = reinterpret_cast<int*>(ls + (size_t)L * TC_QUERIES);
 
@@ -307,7 +307,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
             mbar_init(smem_u32(&bar_free[s]), TC_EPI_WARPS);
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(smem_u32(&bar_acc_full[b]), 1);
+            mbar_init(smem_u32(&bar_acc_full[2 * b]), 1);
+            mbar_init(smem_u32(&bar_acc_full[2 * b + 1]), 1);
             mbar_init(smem_u32(&bar_acc_free[b]), TC_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -411,8 +412,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
                         const uint64_t bdesc = tc_smem_desc(ring_base + (uint32_t)slot * TILE_BYTES + ks * KSTEP_BYTES, lbo, sbo);
                         umma_tf32(d_tmem, adesc, bdesc, TC_IDESC, ks > 0 ? 1u : 0u);
                     }
+                    umma_commit(smem_u32(&bar_acc_full[2 * buf + mb]));   // this query block's warps can start
                 }
-                umma_commit(smem_u32(&bar_acc_full[buf]));
             }
             __syncwarp();
             if (++slot == NS) {
@@ -427,7 +428,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
         for (int it = 0; it < nt; ++it) {
             const int buf = it & 1;
             {
-                const uint32_t fb = smem_u32(&bar_acc_full[buf]);
+                const uint32_t fb = smem_u32(&bar_acc_full[2 * buf + mb]);
                 while (!mbar_try_wait(fb, (uint32_t)(it >> 1) & 1u)) {
                 }
             }
@@ -490,7 +491,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
 }
 
 size_t tc_fixed_smem(int K, int list_len) {
-    return (size_t)2 * K * TC_QBLK * 4 + (size_t)(2 * 8 + 4) * sizeof(uint64_t) + 16 +
+    return (size_t)2 * K * TC_QBLK * 4 + (size_t)(2 * 8 + 6) * sizeof(uint64_t) + 16 +
            (size_t)list_len * TC_QUERIES * (sizeof(float) + sizeof(int));
 }
 

@@ -49,10 +49,10 @@ class Sim:
         self.rng = random.Random(seed)
         self.full = [MBar(1) for _ in range(ns)]
         self.free = [MBar(EPI_WARPS) for _ in range(ns)]
-        self.acc_full = [MBar(1), MBar(1)]
+        self.acc_full = [[MBar(1), MBar(1)], [MBar(1), MBar(1)]]   # [buffer][query block]
         self.acc_free = [MBar(EPI_WARPS), MBar(EPI_WARPS)]
         self.slot_tile = [None] * ns        # tile whose bytes are in the ring slot
-        self.acc_tile = [None, None]        # tile whose scores are in the accumulator buffer
+        self.acc_tile = [[None, None], [None, None]]   # tile whose scores are in the accumulator buffer, per query block
         self.tma_q, self.mma_q = [], []     # asynchronous completions, in issue order per engine
 
     # -- a wait that also checks the waiter is not two phases late -------------------------------
@@ -89,11 +89,12 @@ class Sim:
                 yield from self.wait(self.acc_free[buf], ((it >> 1) - 1) & 1, (it >> 1) - 1)
             assert self.slot_tile[slot] == it, 'MMA read a ring slot holding another tile'
 
-            def finish(slot=slot, it=it, buf=buf):
-                assert self.slot_tile[slot] == it, 'ring slot overwritten while the MMA was reading it'
-                self.acc_tile[buf] = it
-                self.acc_full[buf].arrive()          # tcgen05.commit
-            self.mma_q.append(finish)
+            for mb in range(2):
+                def finish(slot=slot, it=it, buf=buf, mb=mb):
+                    assert self.slot_tile[slot] == it, 'ring slot overwritten while the MMA was reading it'
+                    self.acc_tile[buf][mb] = it
+                    self.acc_full[buf][mb].arrive()  # tcgen05.commit after the MMAs of this query block
+                self.mma_q.append(finish)
             yield
             slot += 1
             if slot == self.ns:
@@ -101,11 +102,12 @@ class Sim:
 
     def epilogue(self, w):
         slot, rnd = 0, 0
+        mb = w >> 2
         for it in range(self.nt):
             buf = it & 1
-            yield from self.wait(self.acc_full[buf], (it >> 1) & 1, it >> 1)
+            yield from self.wait(self.acc_full[buf][mb], (it >> 1) & 1, it >> 1)
             for _ in range(4):                       # four tcgen05.ld groups
-                assert self.acc_tile[buf] == it, 'accumulator buffer overwritten before it was read'
+                assert self.acc_tile[buf][mb] == it, 'accumulator buffer overwritten before it was read'
                 yield
             self.acc_free[buf].arrive()
             # slow path of the last group: reads the operand tile (after observing its TMA barrier)
@@ -143,7 +145,7 @@ class Sim:
                 q.pop(0)()
 
     def snapshot(self):
-        bars = self.full + self.free + self.acc_full + self.acc_free
+        bars = self.full + self.free + self.acc_full[0] + self.acc_full[1] + self.acc_free
         return tuple((b.completed, b.pending, b.tx) for b in bars)
 
 
