@@ -137,6 +137,9 @@ int  mce_ctx_set_option(mce_ctx *ctx, const char *name, int value);
 /* Diagnostics of the last call on this context: "tc_check_ratio" (worst |coarse - exact| / allowance seen by a
    "tc_check" run; must stay below 1), "tc_check_pairs" (pairs compared, modulo 2^32), "filter_engine". */
 int  mce_ctx_get_debug(mce_ctx *ctx, const char *name, double *value);
+/* "tc_dump": after a "tc_check" run, the coarse scores of the first unit's first tile, float[256 queries][128
+   references]; *n receives the element count, `out` may be NULL to query it. */
+int  mce_ctx_get_debug_array(mce_ctx *ctx, const char *name, float *out, int64_t capacity, int64_t *n);
 
 int  mce_evidence(mce_ctx *ctx, const mce_problem *problem, mce_result *result);
 int  mce_evidence_batch(mce_ctx *ctx, int n, const mce_problem *problems, mce_result *results);

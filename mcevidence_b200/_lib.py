@@ -91,6 +91,7 @@ def load_library():
         lib.mce_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         lib.mce_ctx_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         lib.mce_ctx_get_debug.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double)]
+        lib.mce_ctx_get_debug_array.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
         lib.mce_evidence.argtypes = [C.c_void_p, C.POINTER(Problem), C.POINTER(Result)]
         lib.mce_evidence_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(Problem), C.POINTER(Result)]
         lib.mce_knn.argtypes = [C.c_void_p, C.POINTER(Problem), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Stats)]
@@ -172,6 +173,15 @@ class Context:
         return v.value
 
     # ------------------------------------------------------------------
+    def get_debug_array(self, name):
+        """``mce_ctx_get_debug_array``: e.g. ``tc_dump`` -> float32 (256, 128) coarse scores of unit 0, tile 0."""
+        n = C.c_int64(0)
+        _check(self._lib, self._lib.mce_ctx_get_debug_array(self._h, name.encode(), None, 0, C.byref(n)))
+        out = np.empty(n.value, dtype=np.float32)
+        if n.value:
+            _check(self._lib, self._lib.mce_ctx_get_debug_array(self._h, name.encode(), _ptr(out), n.value, C.byref(n)))
+        return out.reshape(-1, 128) if n.value else out
+
     def _problem(self, query, ref, logl, weights, ndim, kmax, W, W_ref, mu, log_jacobian, log_sum_w,
                  log_prior_volume, q_range, flags, keep):
         p = Problem()

@@ -11,6 +11,7 @@
 
 #include <mutex>
 #include <new>
+#include <vector>
 
 using namespace mce;
 
@@ -93,7 +94,8 @@ struct mce_ctx {
     // exactly and record the worst |coarse - exact| / e; slack = percent of the default error allowance
     int opt_engine = 0, opt_tc_check = 0, opt_tc_swap = 0, opt_tc_slack = 100;
     double dbg_tc_ratio = 0.0, dbg_tc_pairs = 0.0;
-    DevBuf xq, xr, logl, w, yr, yq, tiles, tc_tiles, tc_debug, cand_idx, cand_th, dknn, idx, flagged, covpart, redpart, scal,
+    std::vector<float> dbg_tc_dump;   // tc_check: coarse scores of unit 0, tile 0 ([256 queries][128 references])
+    DevBuf xq, xr, logl, w, yr, yq, tiles, tc_tiles, tc_debug, tc_dump, cand_idx, cand_th, dknn, idx, flagged, covpart, redpart, scal,
         sink, exact;
     DevScalars* hscal = nullptr;  // pinned
     cudaEvent_t ev[EV_COUNT] = {};
@@ -452,6 +454,13 @@ int run_problem(mce_ctx* c, const Run& r) {
             tp.slack_qr = (float)(scale * (ldexp(1.0, -9) * (1.0 + ldexp(1.0, -10)) + ldexp(1.0, -14)));
             tp.slack_rr = (float)(scale * 0.5 * (ldexp(1.0, -20) + ldexp(1.0, -14)));
             tp.debug = c->tc_debug.as<unsigned int>();
+            tp.dump = nullptr;
+            if (c->opt_tc_check) {
+                rc = c->tc_dump.ensure((size_t)TC_QUERIES * TC_TILE_REFS * sizeof(float));
+                if (rc) return rc;
+                CU(cudaMemsetAsync(c->tc_dump.p, 0, (size_t)TC_QUERIES * TC_TILE_REFS * sizeof(float), st));
+                tp.dump = c->tc_dump.as<float>();
+            }
             tp.stages = tc_stages;
             tp.swap_offsets = c->opt_tc_swap;
             tp.check = c->opt_tc_check;
@@ -559,6 +568,8 @@ int run_problem(mce_ctx* c, const Run& r) {
         memcpy(&ratio, &dbg[0], 4);
         c->dbg_tc_ratio = ratio;
         c->dbg_tc_pairs = dbg[1];
+        c->dbg_tc_dump.resize((size_t)TC_QUERIES * TC_TILE_REFS);
+        CU(cudaMemcpy(c->dbg_tc_dump.data(), c->tc_dump.p, c->dbg_tc_dump.size() * sizeof(float), cudaMemcpyDeviceToHost));
     }
     if (c->hscal->status != 0)
         return fail(MCE_ERR_NOT_POSDEF,
@@ -668,7 +679,7 @@ void mce_ctx_destroy(mce_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
-    DevBuf* bufs[] = {&c->xq, &c->xr, &c->logl, &c->w, &c->yr, &c->yq, &c->tiles, &c->tc_tiles, &c->tc_debug, &c->cand_idx, &c->cand_th,
+    DevBuf* bufs[] = {&c->xq, &c->xr, &c->logl, &c->w, &c->yr, &c->yq, &c->tiles, &c->tc_tiles, &c->tc_debug, &c->tc_dump, &c->cand_idx, &c->cand_th,
                       &c->dknn, &c->idx, &c->flagged, &c->covpart, &c->redpart, &c->scal, &c->sink, &c->exact};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; ++i)
@@ -715,6 +726,18 @@ int mce_ctx_get_debug(mce_ctx* c, const char* name, double* value) {
     else if (!strcmp(name, "tc_check_pairs")) *value = c->dbg_tc_pairs;
     else if (!strcmp(name, "filter_engine")) *value = c->opt_engine;
     else return fail(MCE_ERR_ARG, "unknown debug value '%s'", name);
+    return MCE_OK;
+}
+
+int mce_ctx_get_debug_array(mce_ctx* c, const char* name, float* out, int64_t capacity, int64_t* n) {
+    if (!c || !name || !n) return fail(MCE_ERR_ARG, "ctx, name or n is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (strcmp(name, "tc_dump")) return fail(MCE_ERR_ARG, "unknown debug array '%s'", name);
+    *n = (int64_t)c->dbg_tc_dump.size();
+    if (out) {
+        if (capacity < *n) return fail(MCE_ERR_ARG, "capacity %lld < %lld", (long long)capacity, (long long)*n);
+        memcpy(out, c->dbg_tc_dump.data(), (size_t)*n * sizeof(float));
+    }
     return MCE_OK;
 }
 

@@ -202,6 +202,7 @@ struct TcEpiState {
     unsigned int checked;
     uint32_t full_bar, full_parity;   // "TMA bytes landed" barrier of the tile being processed
     int d, len, self;
+    float* dump_row;     // CHECK: where this query's coarse scores of the unit's first tile go (or null)
 };
 
 // The epilogue learns about a tile through the accumulator barrier only; before it reads the operand tile
@@ -215,6 +216,10 @@ __device__ __forceinline__ void tc_acquire_tile(const TcEpiState& st) {
 template <bool CHECK>
 __device__ __forceinline__ void tc_process(const uint32_t (&v)[32], int col0, uint32_t tile, int ridx0, TcEpiState& st) {
     if constexpr (CHECK) {
+        if (st.dump_row) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) st.dump_row[col0 + i] = __uint_as_float(v[i]);
+        }
         if (st.th < CUDART_INF_F) {   // valid query
             tc_acquire_tile(st);
 #pragma unroll 1
@@ -316,6 +321,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
     TcEpiState st;
     st.worst = 0.f;
     st.checked = 0;
+    st.dump_row = nullptr;
     const long long ql = (long long)qblock * TC_QUERIES + tid;   // epilogue threads: local query id
     if (warp < TC_EPI_WARPS) {
         const int mb = tid >> 7, row = tid & 127;
@@ -436,6 +442,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
             tc_fence_after();
             st.full_bar = smem_u32(&bar_full[slot]);
             st.full_parity = (uint32_t)round & 1u;
+            if constexpr (CHECK) st.dump_row = (tp.dump && blockIdx.x == 0 && it == 0) ? tp.dump + (size_t)tid * TC_TILE_REFS : nullptr;
             const uint32_t taddr = tlane + (uint32_t)buf * 256u;
             const uint32_t tile = smem_u32(ring) + (uint32_t)slot * TILE_BYTES;
             const int ridx0 = (t0 + it) * TC_TILE_REFS;

@@ -43,6 +43,20 @@ if stage in ('1', '1s'):
     x = rng.normal(size=(300, 3))
     dk, ix, st = ctx.knn(x, 3, identity=True)
     od, oi = oracle_knn(x, 3)
+    # coarse scores of unit 0, tile 0 as the tensor core produced them vs a numpy emulation (TF32-truncated operands)
+    dump = ctx.get_debug_array('tc_dump')
+    def tf32(a):
+        return (np.ascontiguousarray(a, dtype=np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+    xf = x.astype(np.float32)
+    h = (-0.5 * (x * x).sum(1)).astype(np.float32)
+    h_hi = tf32(h); h_lo = tf32(h - h_hi)
+    nqd, nrd = min(256, len(x)), min(128, len(x))
+    want = tf32(xf[:nqd]).astype(np.float64) @ tf32(xf[:nrd]).astype(np.float64).T + h_hi[:nrd].astype(np.float64) + h_lo[:nrd]
+    got = dump[:nqd, :nrd].astype(np.float64) if dump.size else np.zeros_like(want)
+    np.savez(%(out)r + '/tc_dump_stage%%s.npz' %% stage, dump=dump, want=want, x=x)
+    rec.update(dump_max_abs_err=float(np.abs(got - want).max()), dump_rows_ok=int((np.abs(got - want).max(axis=1) < 1e-3).sum()),
+               dump_cols_ok=int((np.abs(got - want).max(axis=0) < 1e-3).sum()), dump_transposed_err=float(
+                   np.abs(got[:min(nqd, nrd), :min(nqd, nrd)].T - want[:min(nqd, nrd), :min(nqd, nrd)]).max()))
     rec.update(idx_equal=bool(np.array_equal(ix, oi)), dist_equal=bool(np.array_equal(dk, od)),
                wrong_rows=int((ix != oi).any(axis=1).sum()), ratio=ctx.get_debug('tc_check_ratio'),
                pairs=ctx.get_debug('tc_check_pairs'), rescanned=int(st['rows_rescanned']), mode=int(st['filter_mode']))
@@ -91,7 +105,7 @@ print('RECORD ' + json.dumps(rec), flush=True)
 
 
 def run_stage(stage, timeout):
-    code = STAGE_CODE % {'root': ROOT, 'stage': stage}
+    code = STAGE_CODE % {'root': ROOT, 'stage': stage, 'out': OUT}
     try:
         r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=timeout, cwd=ROOT)
     except subprocess.TimeoutExpired as e:
