@@ -4,7 +4,8 @@
 
 Every stage runs in its own process under a timeout, so a kernel that spins on a barrier costs one stage, not
 the GPU call.  Stages:
-  1  tiny    300 x 3, tc_check: neighbours vs the FP64 oracle, worst |coarse - exact| / allowance
+  1  tiny    300 x {3, 10, 27}, tc_check: neighbours vs the FP64 oracle, worst |coarse - exact| / allowance, and the
+             dumped coarse scores of the first tile vs a numpy emulation (per K chunk)
   1s the same with the two descriptor byte offsets exchanged (only if stage 1 returns wrong neighbours)
   2  shapes  one case per K padding (ndim 5, 10, 20, 27, 40, 64), auto and cross, split reference set
   3  speed   cfg2 shard / full (N = 1e6, ndim 10) and ndim 27: ms_filter of both engines, identical neighbours
@@ -39,27 +40,43 @@ rec = {'stage': stage}
 if stage in ('1', '1s'):
     ctx.set_option('tc_swap_offsets', 1 if stage == '1s' else 0)
     ctx.set_option('tc_check', 1)
-    rng = np.random.default_rng(1)
-    x = rng.normal(size=(300, 3))
-    dk, ix, st = ctx.knn(x, 3, identity=True)
-    od, oi = oracle_knn(x, 3)
-    # coarse scores of unit 0, tile 0 as the tensor core produced them vs a numpy emulation (TF32-truncated operands)
-    dump = ctx.get_debug_array('tc_dump')
     def tf32(a):
         return (np.ascontiguousarray(a, dtype=np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
-    xf = x.astype(np.float32)
-    h = (-0.5 * (x * x).sum(1)).astype(np.float32)
-    h_hi = tf32(h); h_lo = tf32(h - h_hi)
-    nqd, nrd = min(256, len(x)), min(128, len(x))
-    want = tf32(xf[:nqd]).astype(np.float64) @ tf32(xf[:nrd]).astype(np.float64).T + h_hi[:nrd].astype(np.float64) + h_lo[:nrd]
-    got = dump[:nqd, :nrd].astype(np.float64) if dump.size else np.zeros_like(want)
-    np.savez(%(out)r + '/tc_dump_stage%%s.npz' %% stage, dump=dump, want=want, x=x)
-    rec.update(dump_max_abs_err=float(np.abs(got - want).max()), dump_rows_ok=int((np.abs(got - want).max(axis=1) < 1e-3).sum()),
-               dump_cols_ok=int((np.abs(got - want).max(axis=0) < 1e-3).sum()), dump_transposed_err=float(
-                   np.abs(got[:min(nqd, nrd), :min(nqd, nrd)].T - want[:min(nqd, nrd), :min(nqd, nrd)]).max()))
-    rec.update(idx_equal=bool(np.array_equal(ix, oi)), dist_equal=bool(np.array_equal(dk, od)),
-               wrong_rows=int((ix != oi).any(axis=1).sum()), ratio=ctx.get_debug('tc_check_ratio'),
-               pairs=ctx.get_debug('tc_check_pairs'), rescanned=int(st['rows_rescanned']), mode=int(st['filter_mode']))
+    subs = []
+    for (n, d) in [(300, 3), (300, 10), (300, 27)]:      # K = 8 (one MMA per query block), 16 (two K steps), 32
+        rng = np.random.default_rng(d)
+        x = rng.normal(size=(n, d))
+        dk, ix, st = ctx.knn(x, 3, identity=True)
+        od, oi = oracle_knn(x, 3)
+        # coarse scores of unit 0, tile 0 as the tensor core produced them vs a numpy emulation (TF32-truncated
+        # operands), per 4-wide K chunk: a least-squares fit of the dump on the chunk contributions shows which
+        # chunks the MMAs really read (all ones = the operand layout is understood)
+        dump = ctx.get_debug_array('tc_dump')
+        K = 8 * ((d + 2 + 7) // 8)
+        xf = x.astype(np.float32)
+        h = (-0.5 * (x * x).sum(1)).astype(np.float32)
+        h_hi = tf32(h); h_lo = tf32(h - h_hi)
+        nqd, nrd = min(256, n), min(128, n)
+        A = np.zeros((nqd, K)); B = np.zeros((nrd, K))
+        A[:, :d] = tf32(xf[:nqd]); A[:, d] = 1.0; A[:, d + 1] = 1.0
+        B[:, :d] = tf32(xf[:nrd]); B[:, d] = h_hi[:nrd]; B[:, d + 1] = h_lo[:nrd]
+        parts = np.stack([A[:, 4 * c:4 * c + 4] @ B[:, 4 * c:4 * c + 4].T for c in range(K // 4)])
+        want = parts.sum(0)
+        got = dump[:nqd, :nrd].astype(np.float64) if dump.size else np.zeros_like(want)
+        coef = np.linalg.lstsq(parts.reshape(K // 4, -1).T, got.ravel(), rcond=None)[0]
+        np.savez(%(out)r + '/tc_dump_stage%%s_d%%d.npz' %% (stage, d), dump=dump, want=want, x=x)
+        subs.append(dict(n=n, d=d, K=K, idx_equal=bool(np.array_equal(ix, oi)), dist_equal=bool(np.array_equal(dk, od)),
+                         wrong_rows=int((ix != oi).any(axis=1).sum()), ratio=ctx.get_debug('tc_check_ratio'),
+                         pairs=ctx.get_debug('tc_check_pairs'), rescanned=int(st['rows_rescanned']), mode=int(st['filter_mode']),
+                         dump_max_abs_err=float(np.abs(got - want).max()),
+                         dump_rows_ok=int((np.abs(got - want).max(axis=1) < 1e-3).sum()),
+                         dump_cols_ok=int((np.abs(got - want).max(axis=0) < 1e-3).sum()),
+                         dump_transposed_err=float(np.abs(got[:nrd, :nrd].T - want[:nrd, :nrd]).max()),
+                         chunk_coefficients=[round(float(c), 3) for c in coef]))
+        print(subs[-1], flush=True)
+    rec['cases'] = subs
+    rec['idx_equal'] = all(c['idx_equal'] for c in subs)
+    rec['dist_equal'] = all(c['dist_equal'] for c in subs)
 elif stage == '2':
     ctx.set_option('tc_check', 1)
     cases = []
