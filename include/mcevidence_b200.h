@@ -170,6 +170,11 @@ int  mce_plan_split(int sm_count, int d, int64_t n_query, int64_t n_ref, int lis
    Reports achieved TFLOP/s counting 2 FLOP per lane-FMA, the roofline denominator of the filter. */
 int  mce_fma_peak(mce_ctx *ctx, int variant, int iters, double *tflops, double *ms);
 
+/* Unit peaks behind the tcgen05 engine, measured with the instruction shapes it uses: unit 0 = FMNMX3
+   (lane-operations/s), 1 / 2 = tcgen05.ld 32x32b.x32 with 8 / 4 warps per SM (bytes/s), 3 = tcgen05.mma
+   kind::tf32 M=128 N=128 K=8 from shared memory (FLOP/s). */
+int  mce_unit_peak(mce_ctx *ctx, int unit, int iters, double *rate, double *ms);
+
 /* Host-side chain ingestion (next-row N1): parse a whitespace-separated text chain (`#` comments, blank
    lines skipped) with `nthreads` threads (<= 0: all cores) into a malloc'ed row-major (nrows, ncols) array --
    the np.loadtxt call of MCEvidence.py:564, same correctly-rounded values.  Free with mce_free_host. */

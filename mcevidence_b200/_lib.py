@@ -99,6 +99,7 @@ def load_library():
         lib.mce_finalize.argtypes = [c_double_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_double,
                                      C.c_double, c_double_p, c_double_p]
         lib.mce_fma_peak.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p]
+        lib.mce_unit_peak.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p]
         lib.mce_plan_split.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.POINTER(C.c_int), C.POINTER(C.c_int), c_double_p]
         lib.mce_read_chain_text.argtypes = [C.c_char_p, C.c_int, C.POINTER(c_double_p), c_int64_p, c_int64_p]
@@ -335,6 +336,13 @@ class Context:
         tf, ms = C.c_double(), C.c_double()
         _check(self._lib, self._lib.mce_fma_peak(self._h, int(variant), int(iters), C.byref(tf), C.byref(ms)))
         return tf.value, ms.value
+
+
+    def unit_peak(self, unit, iters=2048):
+        """``mce_unit_peak``: (rate, ms) of FMNMX3 (0), tcgen05.ld with 8 / 4 warps (1 / 2), tf32 tcgen05.mma (3)."""
+        rate, ms = C.c_double(), C.c_double()
+        _check(self._lib, self._lib.mce_unit_peak(self._h, int(unit), int(iters), C.byref(rate), C.byref(ms)))
+        return rate.value, ms.value
 
 
 def combine_partials(parts):

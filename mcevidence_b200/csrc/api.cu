@@ -850,4 +850,28 @@ int mce_fma_peak(mce_ctx* c, int variant, int iters, double* tflops, double* ms_
     return MCE_OK;
 }
 
+int mce_unit_peak(mce_ctx* c, int unit, int iters, double* rate, double* ms_out) {
+    if (!c || !rate) return fail(MCE_ERR_ARG, "ctx or rate is NULL");
+    if (unit < 0 || unit > 3 || iters < 1) return fail(MCE_ERR_ARG, "bad unit/iters");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    int rc = c->sink.ensure((size_t)c->sm_count * 8 * 256 * sizeof(float));
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    int grid = 0;
+    if (launch_unit_peak(unit, iters / 8 + 1, c->sm_count, c->sink.as<float>(), st, &grid) != 0)   // warm-up
+        return fail(MCE_ERR_CUDA, "unit-peak launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    CU(cudaEventRecord(c->ev[EV_START], st));
+    if (launch_unit_peak(unit, iters, c->sm_count, c->sink.as<float>(), st, &grid) != 0)
+        return fail(MCE_ERR_CUDA, "unit-peak launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    CU(cudaEventRecord(c->ev[EV_END], st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, c->ev[EV_START], c->ev[EV_END]));
+    *rate = unit_peak_work(unit, iters, grid) / ((double)ms * 1e-3);
+    if (ms_out) *ms_out = ms;
+    return MCE_OK;
+}
+
 }  // extern "C"

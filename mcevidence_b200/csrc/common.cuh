@@ -171,4 +171,8 @@ void launch_reduce(const ReduceParams& p, int grid, cudaStream_t st, int* launch
 void launch_fma_peak(int variant, int iters, int grid, float* sink, cudaStream_t st);
 long long fma_peak_flops(int variant, int iters, int grid);
 
+// ---- unit peaks of the tensor-core engine (tc_peak.cu): 0 FMNMX3, 1/2 tcgen05.ld (8/4 warps), 3 tcgen05.mma tf32 ----
+int launch_unit_peak(int unit, int iters, int sm_count, float* sink, cudaStream_t st, int* grid_out);
+double unit_peak_work(int unit, int iters, int grid);
+
 }  // namespace mce

@@ -7,6 +7,7 @@ the GPU call.  Stages:
   1  tiny    300 x {3, 10, 27}, tc_check: neighbours vs the FP64 oracle, worst |coarse - exact| / allowance, and the
              dumped coarse scores of the first tile vs a numpy emulation (per K chunk)
   1s the same with the two descriptor byte offsets exchanged (only if stage 1 returns wrong neighbours)
+  p  peaks   FMNMX3, tcgen05.ld and tf32 tcgen05.mma unit rates (mce_unit_peak)
   2  shapes  one case per K padding (ndim 5, 10, 20, 27, 40, 64), auto and cross, split reference set
   3  speed   cfg2 shard / full (N = 1e6, ndim 10) and ndim 27: ms_filter of both engines, identical neighbours
 Results: gpurun_out/tc_bringup.json (one record per stage) and the log on stdout.
@@ -77,6 +78,16 @@ if stage in ('1', '1s'):
     rec['cases'] = subs
     rec['idx_equal'] = all(c['idx_equal'] for c in subs)
     rec['dist_equal'] = all(c['dist_equal'] for c in subs)
+elif stage == 'p':
+    # unit peaks the engine's tile loop is bounded by
+    names = {0: 'fmnmx3_lane_ops_per_s', 1: 'tmem_ld_bytes_per_s_8warps', 2: 'tmem_ld_bytes_per_s_4warps', 3: 'tf32_mma_flop_per_s'}
+    for unit, name in names.items():
+        best = max(ctx.unit_peak(unit, 4096)[0] for _ in range(3))
+        rec[name] = best
+        print(name, '%%.4g' %% best, flush=True)
+    sm, clk = 148, 1.965e9
+    rec['per_sm_per_clk'] = {'fmnmx3_lanes': rec[names[0]] / sm / clk, 'tmem_ld_bytes_8w': rec[names[1]] / sm / clk,
+                             'tmem_ld_bytes_4w': rec[names[2]] / sm / clk, 'tf32_flop': rec[names[3]] / sm / clk}
 elif stage == '2':
     ctx.set_option('tc_check', 1)
     cases = []
@@ -149,6 +160,7 @@ def main():
         r1s = run_stage('1s', 120)
         recs.append(r1s)
         ok = False   # a layout fix is needed before going on
+    recs.append(run_stage('p', 120))
     if ok:
         recs.append(run_stage('2', 300))
         recs.append(run_stage('3', 600))
