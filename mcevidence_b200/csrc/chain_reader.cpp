@@ -1,7 +1,8 @@
 // Host-side chain ingestion: multi-threaded parser for CosmoMC-style
 // whitespace-separated text chains, the `np.loadtxt` call of the reference (MCEvidence.py:564).
-// Decimal -> double conversion is glibc strtod (correctly rounded), i.e. the same values as
-// Python's float() / np.loadtxt; `#` starts a comment; blank lines are skipped.
+// Decimal -> double conversion is std::from_chars (correctly rounded, Eisel-Lemire fast path) with glibc
+// strtod as the fallback for spellings from_chars rejects (leading '+', hexadecimal): the same values
+// as Python's float() / np.loadtxt; `#` starts a comment; blank lines are skipped.
 // Not on the GPU hot path, but after it text parsing dominates "seconds per logE" for grids
 // of small chains (planck_mcevidence.py reads ~4.3e6 rows for 175 evidence calls).
 #include "../../include/mcevidence_b200.h"
@@ -15,6 +16,8 @@
 #include <unistd.h>
 
 #include <atomic>
+#include <charconv>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -165,9 +168,18 @@ int mce_read_chain_text(const char* path, int nthreads, double** data, int64_t* 
                     const char* q = skip_ws(p, de);
                     int c = 0;
                     while (q < de) {
-                        char* stop = nullptr;
-                        const double v = strtod(q, &stop);
-                        if (stop == q || stop > de || c >= cols) {   // not a number / ragged row
+                        double v = 0.0;
+                        const char* stop = q;
+                        const std::from_chars_result fr = std::from_chars(q, de, v);
+                        if (fr.ec == std::errc() && fr.ptr > q) {
+                            stop = fr.ptr;
+                        } else {   // '+1.0', hex floats, out-of-range spellings: glibc decides
+                            char* sp = nullptr;
+                            v = strtod(q, &sp);
+                            stop = sp;
+                        }
+                        if (stop == q || stop > de || c >= cols ||
+                            (stop < de && !(*stop == ' ' || *stop == '\t' || *stop == '\r'))) {   // not a number / ragged row
                             bad.store(1);
                             break;
                         }

@@ -148,7 +148,7 @@ def test_importance_sample_and_burn_partition():
 
 
 def test_native_chain_reader_matches_loadtxt(tmp_path):
-    """mce_read_chain_text (multi-threaded strtod) returns exactly what np.loadtxt returns."""
+    """mce_read_chain_text (multi-threaded from_chars, strtod fallback) returns exactly what np.loadtxt returns."""
     from mcevidence_b200 import _lib
     rng = np.random.default_rng(6)
     x = rng.normal(size=(20000, 9)) * 10.0 ** rng.integers(-20, 20, size=(20000, 9))
@@ -173,3 +173,16 @@ def test_native_chain_reader_matches_loadtxt(tmp_path):
     with open(one, 'w') as fh:
         fh.write('1 2 3 4\n')
     assert read_chain_file(one).shape == (1, 4)
+    # spellings the fast conversion hands to strtod or has to treat like Python's float(): leading '+', inf / nan,
+    # overflow, underflow to a denormal and to zero, bare leading / trailing decimal points, signed zero
+    odd = str(tmp_path / 'odd.txt')
+    with open(odd, 'w') as fh:
+        fh.write('+1.5 -2e3\t3.25E-2 inf\r\n 4 5 6 nan # c\n7.0e+00 8 9 -inf\n 1e-320 1e400 1e-400 -0.0\n.5 5. 1E5 -.25e-1\n')
+    got, want = _lib.read_chain_text(odd, 2), np.loadtxt(odd)
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(np.signbit(got), np.signbit(want))
+    bad = str(tmp_path / 'bad.txt')
+    with open(bad, 'w') as fh:
+        fh.write('1 2x 3\n')
+    with pytest.raises(_lib.MCEError):       # trailing garbage in a token is an error, as in np.loadtxt
+        _lib.read_chain_text(bad)
