@@ -7,6 +7,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -658,6 +659,7 @@ int mce_ctx_create(int device, mce_ctx** out) {
     if (!c) return fail(MCE_ERR_NOMEM, "out of host memory");
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    if (const char* eng = getenv("MCE_FILTER_ENGINE")) c->opt_engine = (eng[0] == '1' && eng[1] == '\0') ? 1 : 0;
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMallocHost(reinterpret_cast<void**>(&c->hscal), sizeof(DevScalars)) != cudaSuccess) {
         const char* msg = cudaGetErrorString(cudaGetLastError());

@@ -5,6 +5,7 @@ Whitened pipeline: r_k within 1e-12 relative of the exact FP64 oracle, logE with
 the reference (the north-star tolerance; the observed differences are ~1e-13, asserted at 1e-9).
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -43,6 +44,7 @@ def test_knn_bit_exact(ctx, n, d, k, cross):
     assert st['launches'] >= 4
 
 
+@pytest.mark.skipif(os.environ.get('MCE_FILTER_ENGINE') == '1', reason='tile options apply to the FFMA engine only')
 @pytest.mark.parametrize('d', [1, 2, 3, 16])
 def test_wide_tile_at_low_ndim(ctx, d):
     """The wide query tile (TQ=4, two-row prefetch; the default for large inputs at ndim <= 16, forced here):
