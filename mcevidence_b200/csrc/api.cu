@@ -93,7 +93,7 @@ struct mce_ctx {
     int opt_tq = -1, opt_tr = -1, opt_packed = -1, opt_chunks = -1, opt_margin = -1, opt_sync = -1, opt_tail = -1;
     // tensor-core engine of the filter (opt-in): 0 = FFMA filter, 1 = tcgen05; check = also evaluate every pair
     // exactly and record the worst |coarse - exact| / e; slack = percent of the default error allowance
-    int opt_engine = 0, opt_tc_check = 0, opt_tc_swap = 0, opt_tc_slack = 100;
+    int opt_engine = 0, opt_tc_check = 0, opt_tc_swap = 0, opt_tc_slack = 100, opt_tc_stages = -1;
     double dbg_tc_ratio = 0.0, dbg_tc_pairs = 0.0;
     std::vector<float> dbg_tc_dump;   // tc_check: coarse scores of unit 0, tile 0 ([256 queries][128 references])
     DevBuf xq, xr, logl, w, yr, yq, tiles, tc_tiles, tc_debug, tc_dump, cand_idx, cand_th, dknn, idx, flagged, covpart, redpart, scal,
@@ -357,7 +357,7 @@ int run_problem(mce_ctx* c, const Run& r) {
     const int ftiles = use_tc ? (int)((n_ref + TC_TILE_REFS - 1) / TC_TILE_REFS) : ntiles;
     const int max_chunks = ftiles / 4 > 1 ? (ftiles / 4 > 64 ? 64 : ftiles / 4) : 1;
     if (use_tc) {
-        if (tc_filter_query(d, list_len, &qpc, &smem, &ctas, &tc_stages) != 0)
+        if (tc_filter_query(d, list_len, c->opt_tc_stages, &qpc, &smem, &ctas, &tc_stages) != 0)
             return fail(MCE_ERR_ARG, "no tensor-core filter for ndim=%d list_len=%d", d, list_len);
         cfg = FilterConfig{1, TC_TILE_REFS, 0, 16};   // reported in the stats: mode 16 = tcgen05 engine
     } else if (c->opt_tq <= 0 && c->opt_tr <= 0 && c->opt_packed < 0 && c->opt_sync < 0 && d <= 16) {
@@ -713,6 +713,7 @@ int mce_ctx_set_option(mce_ctx* c, const char* name, int value) {
         c->opt_engine = value;
     } else if (!strcmp(name, "tc_check")) c->opt_tc_check = value != 0;
     else if (!strcmp(name, "tc_swap_offsets")) c->opt_tc_swap = value != 0;
+    else if (!strcmp(name, "tc_stages")) c->opt_tc_stages = value;
     else if (!strcmp(name, "tc_slack_percent")) {
         if (value < 1) return fail(MCE_ERR_ARG, "tc_slack_percent must be positive");
         c->opt_tc_slack = value;

@@ -120,7 +120,8 @@ size_t tc_image_bytes(long long n_ref, int d);
 void launch_tc_image(const double* y64, const float* ffma_tiles, long long n_ref, int d, float* image, cudaStream_t st,
                      int* launches);
 // Returns 0 and fills the launch shape on success, -1 if the configuration cannot run.
-int tc_filter_query(int d, int list_len, int* queries_per_cta, int* smem_bytes, int* ctas_per_sm, int* stages);
+// want_stages <= 0: as many ring slots (2..8) as fit the shared-memory budget
+int tc_filter_query(int d, int list_len, int want_stages, int* queries_per_cta, int* smem_bytes, int* ctas_per_sm, int* stages);
 int launch_tc_filter(const TcFilterParams& p, cudaStream_t st, int* launches);
 
 // ---- K3: FP64 re-rank + verification, exact re-scan ---------------------------------------

@@ -491,7 +491,7 @@ void launch_tc_image(const double* y64, const float* ffma_tiles, long long n_ref
     *launches += 1;
 }
 
-int tc_filter_query(int d, int list_len, int* queries_per_cta, int* smem_bytes, int* ctas_per_sm, int* stages) {
+int tc_filter_query(int d, int list_len, int want_stages, int* queries_per_cta, int* smem_bytes, int* ctas_per_sm, int* stages) {
     if (d < 1 || d > MAX_DIM) return -1;
     const int K = tc_kpad(d);
     const size_t tile = (size_t)K * TC_TILE_REFS * 4;
@@ -500,6 +500,7 @@ int tc_filter_query(int d, int list_len, int* queries_per_cta, int* smem_bytes, 
     long long ns = ((long long)TC_SMEM_BUDGET - (long long)fixed) / (long long)tile;
     if (ns > 8) ns = 8;
     if (ns < 2) ns = 2;
+    if (want_stages >= 2 && want_stages <= 8 && fixed + (size_t)want_stages * tile <= 227 * 1024) ns = want_stages;
     *queries_per_cta = TC_QUERIES;
     *smem_bytes = (int)(fixed + (size_t)ns * tile);
     *ctas_per_sm = 1;   // a CTA owns all 512 TMEM columns
