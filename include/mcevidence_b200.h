@@ -134,7 +134,8 @@ int  mce_ctx_set_stream(mce_ctx *ctx, void *cuda_stream);
    Diagnostics of engine 1: "tc_check" (1: also evaluate every pair exactly and record the worst
    |coarse - exact| / allowance, read back with mce_ctx_get_debug), "tc_slack_percent" (scales the allowance,
    default 100), "tc_swap_offsets" (exchange the two byte offsets of the shared-memory matrix descriptors),
-   "tc_stages" (shared-memory ring depth 2..8, -1 = as many as fit). */
+   "tc_stages" (shared-memory ring depth 2..8, -1 = as many as fit), "tc_perf_mode" (timing experiments whose
+   results are garbage: 1 = the epilogue skips the TMEM loads, 2 = loads without the threshold test). */
 int  mce_ctx_set_option(mce_ctx *ctx, const char *name, int value);
 /* Diagnostics of the last call on this context: "tc_check_ratio" (worst |coarse - exact| / allowance seen by a
    "tc_check" run; must stay below 1), "tc_check_pairs" (pairs compared, modulo 2^32), "filter_engine". */

@@ -93,7 +93,7 @@ struct mce_ctx {
     int opt_tq = -1, opt_tr = -1, opt_packed = -1, opt_chunks = -1, opt_margin = -1, opt_sync = -1, opt_tail = -1;
     // tensor-core engine of the filter (opt-in): 0 = FFMA filter, 1 = tcgen05; check = also evaluate every pair
     // exactly and record the worst |coarse - exact| / e; slack = percent of the default error allowance
-    int opt_engine = 0, opt_tc_check = 0, opt_tc_swap = 0, opt_tc_slack = 100, opt_tc_stages = -1;
+    int opt_engine = 0, opt_tc_check = 0, opt_tc_swap = 0, opt_tc_slack = 100, opt_tc_stages = -1, opt_tc_perf = 0;
     double dbg_tc_ratio = 0.0, dbg_tc_pairs = 0.0;
     std::vector<float> dbg_tc_dump;   // tc_check: coarse scores of unit 0, tile 0 ([256 queries][128 references])
     DevBuf xq, xr, logl, w, yr, yq, tiles, tc_tiles, tc_debug, tc_dump, cand_idx, cand_th, dknn, idx, flagged, covpart, redpart, scal,
@@ -465,6 +465,7 @@ int run_problem(mce_ctx* c, const Run& r) {
             tp.stages = tc_stages;
             tp.swap_offsets = c->opt_tc_swap;
             tp.check = c->opt_tc_check;
+            tp.perf_mode = c->opt_tc_perf;
             if (launch_tc_filter(tp, st, &launches) != 0)
                 return fail(MCE_ERR_CUDA, "tensor-core filter launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         } else if (launch_filter(fp, cfg, st, &launches) != 0) {
@@ -714,6 +715,7 @@ int mce_ctx_set_option(mce_ctx* c, const char* name, int value) {
     } else if (!strcmp(name, "tc_check")) c->opt_tc_check = value != 0;
     else if (!strcmp(name, "tc_swap_offsets")) c->opt_tc_swap = value != 0;
     else if (!strcmp(name, "tc_stages")) c->opt_tc_stages = value;
+    else if (!strcmp(name, "tc_perf_mode")) c->opt_tc_perf = (value == 1 || value == 2) ? value : 0;
     else if (!strcmp(name, "tc_slack_percent")) {
         if (value < 1) return fail(MCE_ERR_ARG, "tc_slack_percent must be positive");
         c->opt_tc_slack = value;

@@ -114,6 +114,8 @@ struct TcFilterParams {
     int stages;                       // shared-memory ring depth
     int swap_offsets;                 // debug: exchange the leading/stride byte offsets of the descriptors
     int check;                        // 1: evaluate every pair exactly as well and record the worst ratio in debug[]
+    int perf_mode;                    // timing experiments only (results are garbage): 1 = epilogue skips the TMEM loads
+                                      // (MMA + TMA pipeline alone), 2 = loads without the threshold test
 };
 size_t tc_image_bytes(long long n_ref, int d);
 // Builds the TC image from the whitened FP64 rows and the h row of the FFMA tiles (bitwise the same h).

@@ -369,27 +369,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
             const uint32_t taddr = tlane + (uint32_t)buf * 256u;
             const uint32_t tile = smem_u32(ring) + (uint32_t)slot * TILE_BYTES;
             const int ridx0 = (t0 + it) * TC_TILE_REFS;
-            // tcgen05.ld is warp-collective: the warp is re-converged after every (divergent) slow path
-            uint32_t va[32], vb[32];
-            tmem_ld32(taddr, va);
-            tmem_wait_ld(va);
-            tmem_ld32(taddr + 32, vb);
-            tc_process<CHECK>(va, 0, tile, ridx0, st);
-            __syncwarp();
-            tmem_wait_ld(vb);
-            tmem_ld32(taddr + 64, va);
-            tc_process<CHECK>(vb, 32, tile, ridx0, st);
-            __syncwarp();
-            tmem_wait_ld(va);
-            tmem_ld32(taddr + 96, vb);
-            tc_process<CHECK>(va, 64, tile, ridx0, st);
-            __syncwarp();
-            tmem_wait_ld(vb);
-            // the accumulator buffer has been read by this warp: hand it back to the MMA issuer
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bar_acc_free[buf]));
-            tc_process<CHECK>(vb, 96, tile, ridx0, st);
+            if (tp.perf_mode == 0) {
+                // tcgen05.ld is warp-collective: the warp is re-converged after every (divergent) slow path
+                uint32_t va[32], vb[32];
+                tmem_ld32(taddr, va);
+                tmem_wait_ld(va);
+                tmem_ld32(taddr + 32, vb);
+                tc_process<CHECK>(va, 0, tile, ridx0, st);
+                __syncwarp();
+                tmem_wait_ld(vb);
+                tmem_ld32(taddr + 64, va);
+                tc_process<CHECK>(vb, 32, tile, ridx0, st);
+                __syncwarp();
+                tmem_wait_ld(va);
+                tmem_ld32(taddr + 96, vb);
+                tc_process<CHECK>(va, 64, tile, ridx0, st);
+                __syncwarp();
+                tmem_wait_ld(vb);
+                // the accumulator buffer has been read by this warp: hand it back to the MMA issuer
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bar_acc_free[buf]));
+                tc_process<CHECK>(vb, 96, tile, ridx0, st);
+            } else {
+                if (tp.perf_mode == 2) {   // the four loads alone
+                    uint32_t va[32], vb[32];
+                    tmem_ld32(taddr, va);
+                    tmem_ld32(taddr + 32, vb);
+                    tmem_wait_ld(va);
+                    tmem_wait_ld(vb);
+                    st.checked ^= va[0] ^ vb[31];
+                    tmem_ld32(taddr + 64, va);
+                    tmem_ld32(taddr + 96, vb);
+                    tmem_wait_ld(va);
+                    tmem_wait_ld(vb);
+                    st.checked ^= va[5] ^ vb[17];
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bar_acc_free[buf]));
+            }
             // the slow path reads the operand tile: release the ring slot only now
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_free[slot]));
@@ -408,6 +427,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
                 atomicMax(&tp.debug[0], __float_as_uint(st.worst));   // non-negative floats order like their bits
                 atomicAdd(&tp.debug[1], st.checked);
             }
+        } else if (tp.perf_mode == 2 && st.checked == 0x9e3779b9u && tp.debug) {
+            tp.debug[1] = st.checked;   // keeps the loads of the timing experiment alive
         }
     }
 

@@ -121,8 +121,16 @@ elif stage == '3':
                 if best is None or st['ms_filter'] < best['ms_filter']:
                     best = st
             out[eng] = (dk, ix, best)
+        # where the time goes: MMA + TMA pipeline alone (1), plus the TMEM loads (2); results of these runs are garbage
+        perf = {}
+        ctx.set_option('filter_engine', 1)
+        for mode in (1, 2):
+            ctx.set_option('tc_perf_mode', mode)
+            perf[mode] = min(ctx.knn(x, 5, q_range=q_range)[2]['ms_filter'] for _ in range(2))
+        ctx.set_option('tc_perf_mode', 0)
         same = bool(np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][0], out[1][0]))
         runs.append(dict(n=n, d=d, queries=qn or n, ms_filter_ffma=out[0][2]['ms_filter'], ms_filter_tc=out[1][2]['ms_filter'],
+                         ms_mma_tma_only=perf[1], ms_with_tmem_loads=perf[2],
                          same_neighbours=same, rescanned_tc=int(out[1][2]['rows_rescanned']),
                          grid_tc=int(out[1][2]['filter_grid']), chunks_tc=int(out[1][2]['ref_chunks']),
                          smem_tc=int(out[1][2]['filter_smem'])))
