@@ -200,8 +200,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
     uint64_t* bar_full = bars;              // [NS]  TMA bytes of a tile have landed
     uint64_t* bar_free = bars + NS;         // [NS]  all epilogue warps are done with the tile in the slot
     uint64_t* bar_acc_full = bars + 2 * NS; // [2 buffers][2 query blocks]  the MMAs of a tile for a query block have completed
-    uint64_t* bar_acc_free = bars + 2 * NS + 4;   // [2] all epilogue warps have read the accumulator buffer
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 6);
+    uint64_t* bar_acc_free = bars + 2 * NS + 4;   // [2 buffers][2 query blocks]  its four epilogue warps have read the accumulator
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 8);
     float* ls = reinterpret_cast<float*>(tmem_slot + 4);
     int* li = reinterpret_cast<int*>(ls + (size_t)L * TC_QUERIES);
 
@@ -237,7 +237,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
         for (int b = 0; b < 2; ++b) {
             mbar_init(smem_u32(&bar_acc_full[2 * b]), 1);
             mbar_init(smem_u32(&bar_acc_full[2 * b + 1]), 1);
-            mbar_init(smem_u32(&bar_acc_free[b]), TC_EPI_WARPS);
+            mbar_init(smem_u32(&bar_acc_free[2 * b]), TC_EPI_WARPS / 2);
+            mbar_init(smem_u32(&bar_acc_free[2 * b + 1]), TC_EPI_WARPS / 2);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -325,15 +326,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
                 while (!mbar_try_wait(fb, (uint32_t)round & 1u)) {
                 }
             }
-            if (it >= 2) {
-                const uint32_t ab = smem_u32(&bar_acc_free[buf]);
-                while (!mbar_try_wait(ab, (uint32_t)((it >> 1) - 1) & 1u)) {
-                }
-            }
-            tc_fence_after();
-            if (elect_one()) {
 #pragma unroll
-                for (int mb = 0; mb < 2; ++mb) {
+            for (int mb = 0; mb < 2; ++mb) {
+                if (it >= 2) {   // the query block's epilogue warps have drained this buffer (tile it - 2)
+                    const uint32_t ab = smem_u32(&bar_acc_free[2 * buf + mb]);
+                    while (!mbar_try_wait(ab, (uint32_t)((it >> 1) - 1) & 1u)) {
+                    }
+                }
+                tc_fence_after();
+                if (elect_one()) {
                     const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u + (uint32_t)mb * 128u;
 #pragma unroll
                     for (int ks = 0; ks < KSTEPS; ++ks) {
@@ -343,6 +344,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
                     }
                     umma_commit(smem_u32(&bar_acc_full[2 * buf + mb]));   // this query block's warps can start
                 }
+                __syncwarp();
             }
             __syncwarp();
             if (++slot == NS) {
@@ -389,7 +391,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
                 // the accumulator buffer has been read by this warp: hand it back to the MMA issuer
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bar_acc_free[buf]));
+                if (lane == 0) mbar_arrive(smem_u32(&bar_acc_free[2 * buf + mb]));
                 tc_process<CHECK>(vb, 96, tile, ridx0, st);
             } else {
                 if (tp.perf_mode == 2) {   // the four loads alone
@@ -407,7 +409,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bar_acc_free[buf]));
+                if (lane == 0) mbar_arrive(smem_u32(&bar_acc_free[2 * buf + mb]));
             }
             // the slow path reads the operand tile: release the ring slot only now
             __syncwarp();
@@ -442,7 +444,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
 }
 
 size_t tc_fixed_smem(int K, int list_len) {
-    return (size_t)2 * K * TC_QBLK * 4 + (size_t)(2 * 8 + 6) * sizeof(uint64_t) + 16 +
+    return (size_t)2 * K * TC_QBLK * 4 + (size_t)(2 * 8 + 8) * sizeof(uint64_t) + 16 +
            (size_t)list_len * TC_QUERIES * (sizeof(float) + sizeof(int));
 }
 

@@ -50,7 +50,7 @@ class Sim:
         self.full = [MBar(1) for _ in range(ns)]
         self.free = [MBar(EPI_WARPS) for _ in range(ns)]
         self.acc_full = [[MBar(1), MBar(1)], [MBar(1), MBar(1)]]   # [buffer][query block]
-        self.acc_free = [MBar(EPI_WARPS), MBar(EPI_WARPS)]
+        self.acc_free = [[MBar(EPI_WARPS // 2), MBar(EPI_WARPS // 2)] for _ in range(2)]   # [buffer][query block]
         self.slot_tile = [None] * ns        # tile whose bytes are in the ring slot
         self.acc_tile = [[None, None], [None, None]]   # tile whose scores are in the accumulator buffer, per query block
         self.tma_q, self.mma_q = [], []     # asynchronous completions, in issue order per engine
@@ -85,17 +85,17 @@ class Sim:
         for it in range(self.nt):
             buf = it & 1
             yield from self.wait(self.full[slot], rnd & 1, rnd)
-            if it >= 2:
-                yield from self.wait(self.acc_free[buf], ((it >> 1) - 1) & 1, (it >> 1) - 1)
             assert self.slot_tile[slot] == it, 'MMA read a ring slot holding another tile'
-
             for mb in range(2):
+                if it >= 2:
+                    yield from self.wait(self.acc_free[buf][mb], ((it >> 1) - 1) & 1, (it >> 1) - 1)
+
                 def finish(slot=slot, it=it, buf=buf, mb=mb):
                     assert self.slot_tile[slot] == it, 'ring slot overwritten while the MMA was reading it'
                     self.acc_tile[buf][mb] = it
                     self.acc_full[buf][mb].arrive()  # tcgen05.commit after the MMAs of this query block
                 self.mma_q.append(finish)
-            yield
+                yield
             slot += 1
             if slot == self.ns:
                 slot, rnd = 0, rnd + 1
@@ -109,7 +109,7 @@ class Sim:
             for _ in range(4):                       # four tcgen05.ld groups
                 assert self.acc_tile[buf][mb] == it, 'accumulator buffer overwritten before it was read'
                 yield
-            self.acc_free[buf].arrive()
+            self.acc_free[buf][mb].arrive()
             # slow path of the last group: reads the operand tile (after observing its TMA barrier)
             yield from self.wait(self.full[slot], rnd & 1, rnd)
             assert self.slot_tile[slot] == it, 'slow path read a ring slot holding another tile'
@@ -145,7 +145,7 @@ class Sim:
                 q.pop(0)()
 
     def snapshot(self):
-        bars = self.full + self.free + self.acc_full[0] + self.acc_full[1] + self.acc_free
+        bars = self.full + self.free + self.acc_full[0] + self.acc_full[1] + self.acc_free[0] + self.acc_free[1]
         return tuple((b.completed, b.pending, b.tx) for b in bars)
 
 
