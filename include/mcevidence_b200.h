@@ -128,9 +128,10 @@ void mce_ctx_destroy(mce_ctx *ctx);
 int  mce_ctx_set_stream(mce_ctx *ctx, void *cuda_stream);
 /* Tuning knobs: "filter_tq", "filter_tr", "filter_packed", "filter_sync" (kernel mode 0/1/2), "ref_chunks"
    (uniform split of the reference set), "list_margin". -1 = automatic.
-   "filter_engine": 0 = FP32 FFMA filter (default), 1 = tcgen05 tensor-core filter (TF32 coarse scores in TMEM,
+   "filter_engine": 0 = FP32 FFMA filter (default), 2 = choose per problem (tcgen05 for ndim >= 4 and at least
+   2e8 pairs), 1 = tcgen05 tensor-core filter (TF32 coarse scores in TMEM,
    exact FP32 evaluation of the columns that pass; same candidates contract, stats.filter_mode reports 16); the
-   environment variable MCE_FILTER_ENGINE=1 makes 1 the initial value of every new context.
+   environment variable MCE_FILTER_ENGINE=1 (or 2) sets the initial value of every new context.
    Diagnostics of engine 1: "tc_check" (1: also evaluate every pair exactly and record the worst
    |coarse - exact| / allowance, read back with mce_ctx_get_debug), "tc_slack_percent" (scales the allowance,
    default 100), "tc_swap_offsets" (exchange the two byte offsets of the shared-memory matrix descriptors),

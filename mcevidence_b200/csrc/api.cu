@@ -334,7 +334,10 @@ int run_problem(mce_ctx* c, const Run& r) {
                       &launches);
         yq_base = c->yr.as<double>();
     }
-    const bool use_tc = c->opt_engine == 1 && !(p.flags & MCE_FLAG_EXACT_ONLY);
+    // engine 2 = automatic: the tensor-core engine where its coarse stage is selective (ndim >= 4) and the problem is
+    // large enough to amortise a 256-query x 128-reference tile per CTA
+    const bool tc_auto = c->opt_engine == 2 && d >= 4 && (double)nq * (double)n_ref >= 2e8;
+    const bool use_tc = (c->opt_engine == 1 || tc_auto) && !(p.flags & MCE_FLAG_EXACT_ONLY);
     if (use_tc) {
         rc = c->tc_tiles.ensure(tc_image_bytes(n_ref, d));
         if (rc) return rc;
@@ -660,7 +663,7 @@ int mce_ctx_create(int device, mce_ctx** out) {
     if (!c) return fail(MCE_ERR_NOMEM, "out of host memory");
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    if (const char* eng = getenv("MCE_FILTER_ENGINE")) c->opt_engine = (eng[0] == '1' && eng[1] == '\0') ? 1 : 0;
+    if (const char* eng = getenv("MCE_FILTER_ENGINE")) c->opt_engine = ((eng[0] == '1' || eng[0] == '2') && eng[1] == '\0') ? eng[0] - '0' : 0;
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMallocHost(reinterpret_cast<void**>(&c->hscal), sizeof(DevScalars)) != cudaSuccess) {
         const char* msg = cudaGetErrorString(cudaGetLastError());
@@ -710,7 +713,7 @@ int mce_ctx_set_option(mce_ctx* c, const char* name, int value) {
     else if (!strcmp(name, "filter_sync")) c->opt_sync = value;
     else if (!strcmp(name, "tail_chunks")) c->opt_tail = value;
     else if (!strcmp(name, "filter_engine")) {
-        if (value != 0 && value != 1) return fail(MCE_ERR_ARG, "filter_engine must be 0 (FFMA) or 1 (tcgen05)");
+        if (value < 0 || value > 2) return fail(MCE_ERR_ARG, "filter_engine must be 0 (FFMA), 1 (tcgen05) or 2 (automatic)");
         c->opt_engine = value;
     } else if (!strcmp(name, "tc_check")) c->opt_tc_check = value != 0;
     else if (!strcmp(name, "tc_swap_offsets")) c->opt_tc_swap = value != 0;
