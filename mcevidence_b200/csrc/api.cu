@@ -334,10 +334,19 @@ int run_problem(mce_ctx* c, const Run& r) {
                       &launches);
         yq_base = c->yr.as<double>();
     }
-    // engine 2 = automatic: the tensor-core engine where its coarse stage is selective (ndim >= 4) and the problem is
-    // large enough to amortise a 256-query x 128-reference tile per CTA
-    const bool tc_auto = c->opt_engine == 2 && d >= 4 && (double)nq * (double)n_ref >= 2e8;
-    const bool use_tc = (c->opt_engine == 1 || tc_auto) && !(p.flags & MCE_FLAG_EXACT_ONLY);
+    // engine 2 = automatic: the tensor-core engine where its coarse stage is selective (ndim >= 4), the problem is
+    // large enough to amortise a 256-query x 128-reference tile per CTA, and its shared-memory footprint fits
+    bool use_tc = false;
+    if ((c->opt_engine == 1 || c->opt_engine == 2) && !(p.flags & MCE_FLAG_EXACT_ONLY)) {
+        int q0 = 0, s0 = 0, c0 = 0, st0 = 0;
+        const bool fits = tc_filter_query(d, K + (c->opt_margin >= 0 ? c->opt_margin : 2), c->opt_tc_stages, &q0, &s0, &c0, &st0) == 0;
+        if (c->opt_engine == 1) {
+            if (!fits) return fail(MCE_ERR_ARG, "no tensor-core filter for ndim=%d with %d neighbours", d, K);
+            use_tc = true;
+        } else {
+            use_tc = fits && d >= 4 && (double)nq * (double)n_ref >= 2e8;
+        }
+    }
     if (use_tc) {
         rc = c->tc_tiles.ensure(tc_image_bytes(n_ref, d));
         if (rc) return rc;
