@@ -131,8 +131,7 @@ struct TcEpiState {
 // The epilogue learns about a tile through the accumulator barrier only; before it reads the operand tile
 // itself it observes the tile's own TMA barrier (already complete, so this never spins).
 __device__ __forceinline__ void tc_acquire_tile(const TcEpiState& st) {
-    while (!mbar_try_wait(st.full_bar, st.full_parity)) {
-    }
+    tc_wait(st.full_bar, st.full_parity);
 }
 
 // one group of 32 columns [col0, col0 + 32) of the tile at `tile`
@@ -302,8 +301,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
             for (int n = 0; n < nt; ++n) {
                 if (round > 0) {
                     const uint32_t fb = smem_u32(&bar_free[slot]);
-                    while (!mbar_try_wait(fb, (uint32_t)(round - 1) & 1u)) {
-                    }
+                    tc_wait(fb, (uint32_t)(round - 1) & 1u);
                 }
                 const uint32_t bar = smem_u32(&bar_full[slot]);
                 mbar_arrive_expect_tx(bar, TILE_BYTES);
@@ -323,15 +321,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
             const int buf = it & 1;
             {
                 const uint32_t fb = smem_u32(&bar_full[slot]);
-                while (!mbar_try_wait(fb, (uint32_t)round & 1u)) {
-                }
+                tc_wait(fb, (uint32_t)round & 1u);
             }
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb) {
                 if (it >= 2) {   // the query block's epilogue warps have drained this buffer (tile it - 2)
                     const uint32_t ab = smem_u32(&bar_acc_free[2 * buf + mb]);
-                    while (!mbar_try_wait(ab, (uint32_t)((it >> 1) - 1) & 1u)) {
-                    }
+                    tc_wait(ab, (uint32_t)((it >> 1) - 1) & 1u);
                 }
                 tc_fence_after();
                 if (elect_one()) {
@@ -360,8 +356,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
             const int buf = it & 1;
             {
                 const uint32_t fb = smem_u32(&bar_acc_full[2 * buf + mb]);
-                while (!mbar_try_wait(fb, (uint32_t)(it >> 1) & 1u)) {
-                }
+                tc_wait(fb, (uint32_t)(it >> 1) & 1u);
             }
             __syncwarp();   // lanes may leave the spin loop at different times
             tc_fence_after();

@@ -100,8 +100,7 @@ __global__ void __launch_bounds__(128, 1) mma_peak_kernel(float* sink, int iters
             umma_commit(smem_u32(&bar));
         }
         __syncwarp();
-        while (!mbar_try_wait(smem_u32(&bar), 0)) {
-        }
+        tc_wait(smem_u32(&bar), 0);
     }
     tc_fence_before();
     __syncthreads();

@@ -84,4 +84,28 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
     return r;
 }
 
+
+// Wait on an mbarrier phase.  A protocol error would otherwise spin for ever and hang the GPU: after about
+// two seconds without progress the kernel traps, which the host reports as a failed launch.
+__device__ __forceinline__ bool tc_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tc_wait(uint32_t bar, uint32_t parity) {
+    if (tc_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!tc_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+
 }  // namespace mce
