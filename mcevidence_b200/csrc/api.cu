@@ -148,9 +148,9 @@ struct Run {
 // Returns T * (queries resident per SM) / (relative pair rate): comparable between tile shapes.
 struct SplitPlan { int nfull, chunks; double cost; };
 SplitPlan plan_split(long long nqblocks, int sm_count, int qpc, int ctas, long long n_ref, int list_len, int d,
-                     bool wide, int max_chunks) {
+                     bool wide, int max_chunks, double kappa_override = 0.0) {
     const long long slots = (long long)sm_count * ctas;
-    const double kappa = (wide ? 500.0 : 250.0) * 11.5 / (d + 1.5);
+    const double kappa = kappa_override > 0.0 ? kappa_override : (wide ? 500.0 : 250.0) * 11.5 / (d + 1.5);
     auto unit = [&](double m) { return m + kappa * list_len * log(fmax(m / list_len, 2.0)); };
     const long long nf = (nqblocks / slots) * slots;
     const long long rem = nqblocks - nf;
@@ -410,7 +410,10 @@ int run_problem(mce_ctx* c, const Run& r) {
         chunks = c->opt_tail;        // whole-set units for the full waves, forced split of the remainder
         nfull = (int)((nqblocks / slots) * slots);
     } else {
-        const SplitPlan pl = plan_split(nqblocks, c->sm_count, qpc, ctas, n_ref, list_len, d, cfg.tq >= 4, max_chunks);
+        // tensor-core engine: a pair costs about 1/100 cycle per SM whatever ndim is, a slow-path visit a few hundred
+        // warp cycles, i.e. relatively far more than in the FFMA filter (a guess until it is calibrated on hardware)
+        const SplitPlan pl = plan_split(nqblocks, c->sm_count, qpc, ctas, n_ref, list_len, d, cfg.tq >= 4, max_chunks,
+                                        use_tc ? 1500.0 : 0.0);
         chunks = pl.chunks;
         nfull = pl.nfull;
     }
