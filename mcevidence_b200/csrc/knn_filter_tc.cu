@@ -98,13 +98,22 @@ __device__ __forceinline__ float tc_list_insert(uint32_t ls, uint32_t li, int le
 // Exact FP32 score from the FP32 words of the operand tiles: the FMA chain of the FFMA filter
 // (accumulator initialised with h, coordinates in order).  Element k of a row sits
 // (k >> 2) * TC_CHUNK_BYTES + (k & 3) * 4 bytes after the row's first 16-byte chunk.
+__device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
 __device__ __forceinline__ float tc_exact_score(uint32_t arow, uint32_t bcol, int d) {
     const float h = lds_f32(bcol + (d >> 2) * TC_CHUNK_BYTES + (d & 3) * 4) +
                     lds_f32(bcol + ((d + 1) >> 2) * TC_CHUNK_BYTES + ((d + 1) & 3) * 4);
-    float acc = fmaf(lds_f32(arow), lds_f32(bcol), h);
-    for (int c = 1; c < d; ++c) {
-        const uint32_t o = (c >> 2) * TC_CHUNK_BYTES + (c & 3) * 4;
-        acc = fmaf(lds_f32(arow + o), lds_f32(bcol + o), acc);
+    float acc = h;
+    for (int c0 = 0; c0 < d; c0 += 4) {   // one 16-byte chunk of both rows per step, coordinates in order
+        const float4 a = lds_f32x4(arow + (c0 >> 2) * TC_CHUNK_BYTES);
+        const float4 b = lds_f32x4(bcol + (c0 >> 2) * TC_CHUNK_BYTES);
+        acc = fmaf(a.x, b.x, acc);
+        if (c0 + 1 < d) acc = fmaf(a.y, b.y, acc);
+        if (c0 + 2 < d) acc = fmaf(a.z, b.z, acc);
+        if (c0 + 3 < d) acc = fmaf(a.w, b.w, acc);
     }
     return acc;
 }
