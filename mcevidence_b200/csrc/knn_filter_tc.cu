@@ -133,14 +133,18 @@ struct TcEpiState {
     float worst;         // CHECK: max |coarse - exact| / e over the pairs of this thread
     unsigned int checked;
     uint32_t full_bar, full_parity;   // "TMA bytes landed" barrier of the tile being processed
+    bool acquired;                    // ... already observed by this thread
     int d, len, self;
     float* dump_row;     // CHECK: where this query's coarse scores of the unit's first tile go (or null)
 };
 
 // The epilogue learns about a tile through the accumulator barrier only; before it reads the operand tile
 // itself it observes the tile's own TMA barrier (already complete, so this never spins).
-__device__ __forceinline__ void tc_acquire_tile(const TcEpiState& st) {
-    tc_wait(st.full_bar, st.full_parity);
+__device__ __forceinline__ void tc_acquire_tile(TcEpiState& st) {
+    if (!st.acquired) {
+        tc_wait(st.full_bar, st.full_parity);
+        st.acquired = true;
+    }
 }
 
 // one group of 32 columns [col0, col0 + 32) of the tile at `tile`
@@ -371,6 +375,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
             tc_fence_after();
             st.full_bar = smem_u32(&bar_full[slot]);
             st.full_parity = (uint32_t)round & 1u;
+            st.acquired = false;
             if constexpr (CHECK) st.dump_row = (tp.dump && blockIdx.x == 0 && it == 0) ? tp.dump + (size_t)tid * TC_TILE_REFS : nullptr;
             const uint32_t taddr = tlane + (uint32_t)buf * 256u;
             const uint32_t tile = smem_u32(ring) + (uint32_t)slot * TILE_BYTES;
