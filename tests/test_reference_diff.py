@@ -116,3 +116,43 @@ def test_host_interface_matches_live_reference(ref, oracle_ctx, tmp_path, seed):
     both_finite = np.isfinite(want)
     assert np.array_equal(np.isfinite(got), both_finite)
     assert np.abs(got[both_finite] - want[both_finite]).max(initial=0.0) < 1e-8
+
+
+@pytest.mark.filterwarnings('ignore::DeprecationWarning')
+@pytest.mark.parametrize('seed', range(20))
+def test_params_info_matches_live_reference(ref, tmp_path, seed):
+    """Parameter selection and prior volume from CosmoMC .ranges and MontePython log.param files
+    (MCEvidence.py:1204-1272) on random files with numeric bounds, degenerate (fixed) parameters and both values of
+    ``cosmo``.  (Unbounded ``N`` entries cannot be compared: the reference fails on them)"""
+    from mcevidence_b200 import priors
+    rng = np.random.default_rng(500 + seed)
+    pool = list(priors.cosmo_params_list[:12]) + ['nuis%d' % i for i in range(8)] + ['calPlanck', 'acib217']
+    names = [pool[i] for i in rng.permutation(len(pool))[:int(rng.integers(2, 14))]]
+    root = str(tmp_path / 'run')
+    cosmomc = bool(rng.integers(0, 2))
+    if cosmomc:
+        with open(root + '.ranges', 'w') as fh:
+            for nm in names:
+                lo = float(np.round(rng.normal() * 10.0 ** rng.integers(-3, 3), 6))
+                hi = lo if rng.random() < 0.25 else lo + float(np.round(abs(rng.normal()) + 0.01, 6)) * 10.0 ** rng.integers(-3, 3)
+                fh.write('%-16s %.8E %.8E\n' % (nm, lo, hi))
+        fname = root
+    else:
+        os.makedirs(root)
+        with open(os.path.join(root, 'log.param'), 'w') as fh:
+            fh.write('#-----CLASS-----\ndata.experiments=[\'fake\']\n')
+            for nm in names:
+                role = ['cosmo', 'nuisance', 'derived'][int(rng.integers(0, 3))]
+                lo = float(np.round(rng.normal(), 4))
+                hi = lo + float(np.round(abs(rng.normal()) + 0.01, 4))
+                fh.write("data.parameters['%s'] = [%g, %g, %g, 0.1, 1, '%s']\n" % (nm, 0.5 * (lo + hi), lo, hi, role))
+            fh.write("# data.parameters['commented'] = [1, 0, 2, 0.1, 1, 'cosmo']\n")
+        fname = root
+    for cosmo in (False, True):
+        want = ref.params_info(fname, cosmo=cosmo)
+        got = priors.params_info(fname, cosmo=cosmo)
+        assert [str(n) for n in got['name']] == [n.decode() if isinstance(n, bytes) else str(n) for n in want['name']]
+        for key in ('min', 'max', 'range'):
+            np.testing.assert_array_equal(np.asarray(got[key], dtype=float), np.asarray(want[key], dtype=float))
+        assert got['ndim'] == want['ndim'] and got['nr_of_params'] == want['nr_of_params']
+        assert got['volume'] == want['volume']
