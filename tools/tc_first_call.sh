@@ -10,7 +10,7 @@ tail -n 40 gpurun_out/tc_bringup.log
 if ! python - <<'PY'
 import json, sys
 recs = json.load(open('gpurun_out/tc_bringup.json'))
-ok = bool(recs and recs[0].get('idx_equal') and recs[0].get('dist_equal'))
+ok = any(r.get('stage') == '1' and r.get('idx_equal') and r.get('dist_equal') for r in recs)
 sys.exit(0 if ok else 1)
 PY
 then
