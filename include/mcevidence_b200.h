@@ -134,7 +134,8 @@ int  mce_ctx_set_stream(mce_ctx *ctx, void *cuda_stream);
    environment variable MCE_FILTER_ENGINE=1 (or 2) sets the initial value of every new context.
    Diagnostics of engine 1: "tc_check" (1: also evaluate every pair exactly and record the worst
    |coarse - exact| / allowance, read back with mce_ctx_get_debug), "tc_slack_percent" (scales the allowance,
-   default 100), "tc_swap_offsets" (exchange the two byte offsets of the shared-memory matrix descriptors),
+   default 100), "tc_swap_offsets" (bit 0: exchange the two byte offsets of the shared-memory matrix descriptors, bit 1: descriptor
+   version field 0),
    "tc_stages" (shared-memory ring depth 2..8, -1 = as many as fit), "tc_perf_mode" (timing experiments whose
    results are garbage: 1 = the epilogue skips the TMEM loads, 2 = loads without the threshold test). */
 int  mce_ctx_set_option(mce_ctx *ctx, const char *name, int value);

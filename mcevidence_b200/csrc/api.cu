@@ -728,7 +728,7 @@ int mce_ctx_set_option(mce_ctx* c, const char* name, int value) {
         if (value < 0 || value > 2) return fail(MCE_ERR_ARG, "filter_engine must be 0 (FFMA), 1 (tcgen05) or 2 (automatic)");
         c->opt_engine = value;
     } else if (!strcmp(name, "tc_check")) c->opt_tc_check = value != 0;
-    else if (!strcmp(name, "tc_swap_offsets")) c->opt_tc_swap = value != 0;
+    else if (!strcmp(name, "tc_swap_offsets")) c->opt_tc_swap = value & 3;   // bit 0: exchange the offsets, bit 1: version field 0
     else if (!strcmp(name, "tc_stages")) c->opt_tc_stages = value;
     else if (!strcmp(name, "tc_perf_mode")) c->opt_tc_perf = (value == 1 || value == 2) ? value : 0;
     else if (!strcmp(name, "tc_slack_percent")) {

@@ -112,7 +112,7 @@ struct TcFilterParams {
     unsigned int* debug;              // CHECK builds: [0] max over pairs of |coarse - exact| / e as float bits, [1] pairs checked (mod 2^32)
     float* dump;                      // CHECK builds: coarse scores of unit 0, tile 0: [TC_QUERIES][TC_TILE_REFS] (may be null)
     int stages;                       // shared-memory ring depth
-    int swap_offsets;                 // debug: exchange the leading/stride byte offsets of the descriptors
+    int swap_offsets;                 // debug bits: 1 = exchange the leading/stride byte offsets of the descriptors, 2 = version field 0
     int check;                        // 1: evaluate every pair exactly as well and record the worst ratio in debug[]
     int perf_mode;                    // timing experiments only (results are garbage): 1 = epilogue skips the TMEM loads
                                       // (MMA + TMA pipeline alone), 2 = loads without the threshold test

@@ -327,8 +327,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
         }
     } else if (warp == TC_MMA_WARP) {
         const uint32_t a_base = smem_u32(a_sm), ring_base = smem_u32(ring);
-        const uint32_t lbo = tp.swap_offsets ? TC_ROWGROUP_BYTES : TC_CHUNK_BYTES;
-        const uint32_t sbo = tp.swap_offsets ? TC_CHUNK_BYTES : TC_ROWGROUP_BYTES;
+        // debug bits of swap_offsets: 1 = exchange the two byte offsets, 2 = descriptor version field 0 instead of 1
+        const uint32_t lbo = (tp.swap_offsets & 1) ? TC_ROWGROUP_BYTES : TC_CHUNK_BYTES;
+        const uint32_t sbo = (tp.swap_offsets & 1) ? TC_CHUNK_BYTES : TC_ROWGROUP_BYTES;
+        const uint32_t dver = (tp.swap_offsets & 2) ? 0u : 1u;
         int slot = 0, round = 0;
         for (int it = 0; it < nt; ++it) {
             const int buf = it & 1;
@@ -347,8 +349,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
                     const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u + (uint32_t)mb * 128u;
 #pragma unroll
                     for (int ks = 0; ks < KSTEPS; ++ks) {
-                        const uint64_t adesc = tc_smem_desc(a_base + mb * A_MB_BYTES + ks * KSTEP_BYTES, lbo, sbo);
-                        const uint64_t bdesc = tc_smem_desc(ring_base + (uint32_t)slot * TILE_BYTES + ks * KSTEP_BYTES, lbo, sbo);
+                        const uint64_t adesc = tc_smem_desc(a_base + mb * A_MB_BYTES + ks * KSTEP_BYTES, lbo, sbo, dver);
+                        const uint64_t bdesc = tc_smem_desc(ring_base + (uint32_t)slot * TILE_BYTES + ks * KSTEP_BYTES, lbo, sbo, dver);
                         umma_tf32(d_tmem, adesc, bdesc, TC_IDESC, ks > 0 ? 1u : 0u);
                     }
                     umma_commit(smem_u32(&bar_acc_full[2 * buf + mb]));   // this query block's warps can start

@@ -19,9 +19,9 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
 
 // shared-memory matrix descriptor, K-major, no swizzle: 8 rows x 16 bytes core matrices; `lbo` = byte distance
 // between core matrices adjacent in K, `sbo` = between core matrices adjacent in M/N; bit 46 = sm_100 version
-__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t version = 1) {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | ((uint64_t)(version & 3u) << 46);
 }
 
 // D[tmem] (+)= A[smem] . B[smem]^T, issued by one thread for the CTA

@@ -6,7 +6,8 @@ Every stage runs in its own process under a timeout, so a kernel that spins on a
 the GPU call.  Stages:
   1  tiny    300 x {3, 10, 27}, tc_check: neighbours vs the FP64 oracle, worst |coarse - exact| / allowance, and the
              dumped coarse scores of the first tile vs a numpy emulation (per K chunk)
-  1s the same with the two descriptor byte offsets exchanged (only if stage 1 returns wrong neighbours)
+  1s/1v/1sv the same with the two descriptor byte offsets exchanged / descriptor version field 0 / both (only if
+     stage 1 returns wrong neighbours)
   p  peaks   FMNMX3, tcgen05.ld and tf32 tcgen05.mma unit rates (mce_unit_peak)
   2  shapes  one case per K padding (ndim 5, 10, 20, 27, 40, 64), auto and cross, split reference set
   3  speed   cfg2 shard / full (N = 1e6, ndim 10) and ndim 27: ms_filter of both engines, identical neighbours
@@ -38,8 +39,8 @@ stage = %(stage)r
 ctx = L.default_context(0)
 ctx.set_option('filter_engine', 1)
 rec = {'stage': stage}
-if stage in ('1', '1s'):
-    ctx.set_option('tc_swap_offsets', 1 if stage == '1s' else 0)
+if stage in ('1', '1s', '1v', '1sv'):
+    ctx.set_option('tc_swap_offsets', {'1': 0, '1s': 1, '1v': 2, '1sv': 3}[stage])
     ctx.set_option('tc_check', 1)
     def tf32(a):
         return (np.ascontiguousarray(a, dtype=np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
@@ -166,7 +167,8 @@ def main():
     recs.append(r1)
     ok = r1.get('idx_equal') and r1.get('dist_equal')
     if not ok and not r1.get('timeout'):
-        recs.append(run_stage('1s', 180))
+        for alt in ('1s', '1v', '1sv'):      # descriptor alternatives: offsets exchanged, version field 0, both
+            recs.append(run_stage(alt, 180))
         ok = False   # a layout fix is needed before going on
     if ok:
         recs.append(run_stage('2', 300))
