@@ -42,7 +42,7 @@ class data_set(object):
         self.adjusted_weights = d['aweights']
 
 
-def read_chain_file(fname):
+def read_chain_file(fname, nthreads=0):
     """Parse a whitespace-separated chain file into a C-contiguous float64 ``(rows, columns)`` array.
 
     Same values as the reference's ``np.loadtxt`` (``MCEvidence.py:564``: correctly rounded
@@ -52,9 +52,21 @@ def read_chain_file(fname):
     """
     try:
         from . import _lib
-        return _lib.read_chain_text(fname)
+        return _lib.read_chain_text(fname, nthreads)
     except Exception:
         return np.ascontiguousarray(np.atleast_2d(np.loadtxt(fname)), dtype=np.float64)
+
+
+_READ_POOL = None
+
+
+def _read_pool():
+    """Process-wide pool of file-reading threads (created on first use; a grid run reads hundreds of roots)."""
+    global _READ_POOL
+    if _READ_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _READ_POOL = ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1), thread_name_prefix='mce-read')
+    return _READ_POOL
 
 
 class SamplesMIXIN(object):
@@ -313,11 +325,15 @@ class MCSamples(SamplesMIXIN):
         self.setup(str_or_dict, **kwargs)
 
     def read_list_to_array(self, flist):
-        chains = []
+        """The chain files of one root, parsed concurrently (the parser releases the GIL): a root is typically
+        4-8 files of about a megabyte, too small for the threads of a single parse to pay off."""
         for f in flist:
             self.logger.info('loading: ' + f)
-            chains.append(read_chain_file(f))
-        return chains
+        if len(flist) == 1:
+            return [read_chain_file(flist[0])]
+        ncpu = os.cpu_count() or 1
+        per_file = max(1, ncpu // len(flist))
+        return list(_read_pool().map(lambda f: read_chain_file(f, per_file), flist))
 
     def load_from_file(self, fname, **kwargs):
         """``fname``: a file, a list of files, a wildcard, or a CosmoMC root (``root_?.txt``;
