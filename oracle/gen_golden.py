@@ -7,6 +7,7 @@ chains.  ``/root/reference`` does not exist on the GPU box, hence the frozen
 fixtures.  Usage::
 
     python oracle/gen_golden.py            # rewrites tests/golden/*.npz
+    python oracle/gen_golden.py NAME ...   # only the named fixtures
 
 Each fixture stores the input chain(s), the call arguments and what the
 reference returned (``MLE`` per k; for the small cases also ``DkNN`` and
@@ -65,8 +66,13 @@ class KnnSpy:
 FMT = '%.10e'
 
 
+ONLY = set()      # names given on the command line: regenerate just these fixtures
+
+
 def run_case(ref, name, chains, np_seed, keep_knn=False, evidence_kwargs=None, as_files=False, **ctor):
     """Run the reference on ``chains`` (arrays, or files ``root_<i>.txt`` when ``as_files``)."""
+    if ONLY and name not in ONLY:
+        return
     evidence_kwargs = evidence_kwargs or {}
     if as_files:
         import tempfile
@@ -172,6 +178,24 @@ def main():
     c, _ = gaussian_chain(3200, 5, seed=92, mean_shift=0.4)
     run_case(ref, 'cross_d5_covsingle', [c], 111, kmax=3, split=True, evidence_kwargs={'covtype': 'single'})
 
+    # Whole-number thinning (thinlen >= 1, an int: a float breaks np.linspace / slicing under current numpy).
+    # Integer weights: getdist's algorithm (MCEvidence.py:481-532).  It uses the removed alias np.int, and the bare
+    # `except` at :283 would silently route the call to weighted_thin instead; the alias is restored for these two
+    # runs so that the unmodified source follows the path it specifies (same kind of shim as DistanceMetric).
+    added_alias = not hasattr(np, 'int')
+    if added_alias:
+        np.int = int
+    try:
+        c, _ = gaussian_chain(4000, 4, seed=95, integer_weights=True, inflate=1.0)
+        run_case(ref, 'auto_d4_file_int_thin', [c], 112, as_files=True, kmax=3, burnlen=200, thinlen=3)
+        # non-integer weights: the heaviest sample of each bin (weighted_thin, MCEvidence.py:447-479)
+        c, _ = gaussian_chain(4000, 4, seed=96, mean_shift=0.3)
+        run_case(ref, 'auto_d4_file_weighted_thin', [c], 113, as_files=True, kmax=3, burnlen=0.2, thinlen=4)
+    finally:
+        if added_alias:
+            del np.int
+
 
 if __name__ == '__main__':
+    ONLY.update(sys.argv[1:])      # python oracle/gen_golden.py [fixture names]: default = all
     main()

@@ -17,6 +17,7 @@ then
     echo "bring-up stage 1 failed: see gpurun_out/tc_bringup.json and gpurun_out/tc_dump_stage*.npz"
     exit 0
 fi
+MCE_TEST_NEW_GOLDEN=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k golden_reference_outputs 2>&1 | tail -n 5 | tee gpurun_out/new_golden.log
 MCE_TEST_TC=1 timeout 600 python -m pytest tests/test_gpu_tc.py -m gpu -x -q 2>&1 | tail -n 15 | tee gpurun_out/tc_tests.log
 # the whole GPU suite on the tensor-core engine
 MCE_FILTER_ENGINE=1 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -n 15 | tee gpurun_out/tc_suite.log
