@@ -18,10 +18,12 @@ from argparse import ArgumentParser
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 from mcevidence_b200 import priors as _priors                       # noqa: E402
-from mcevidence_b200.chains import FORMAT, MCSamples, SamplesMIXIN, data_set   # noqa: E402,F401
+from mcevidence_b200.chains import FORMAT, LoggingHandler, MCSamples, SamplesMIXIN, data_set   # noqa: E402,F401
 from mcevidence_b200.evidence import MCEvidence                      # noqa: E402,F401
-from mcevidence_b200.priors import (cosmo_params_list, get_prior_volume, iscosmo_param,   # noqa: E402,F401
-                                    params_info)
+from mcevidence_b200.priors import (cosmo_params_list, extract_array, extract_dict, get_prior_volume,   # noqa: E402,F401
+                                    iscosmo_param, params_info, query_yes_no)
+
+use_getdist = False      # the reference's import probe (MCEvidence.py:50-59); getdist is never needed here
 
 __version_info__ = ('17', '04', '2018')          # interface version of the reference this mirrors
 __version__ = '-'.join(__version_info__)

@@ -57,6 +57,18 @@ def read_chain_file(fname, nthreads=0):
         return np.ascontiguousarray(np.atleast_2d(np.loadtxt(fname)), dtype=np.float64)
 
 
+class LoggingHandler(object):
+    """Mixin of the reference (``MCEvidence.py:91-97``): ``set_logger`` attaches a logger named after the calling
+    source line."""
+
+    def set_logger(self):
+        self.logger = logging.getLogger(self.log_message())
+
+    def log_message(self):
+        import inspect
+        return str(inspect.stack()[2][4])
+
+
 _READ_POOL = None
 
 

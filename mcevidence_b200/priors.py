@@ -59,6 +59,48 @@ def _parse_logparam_line(line):
     return name, vals
 
 
+def extract_array(line):
+    """Right-hand side of a MontePython ``name = [a, b, 'c']`` line as a list of int / float / str items
+    (``MCEvidence.py:1173-1185``)."""
+    rhs = line.split('=')[-1].strip()
+    items = [tok.strip().strip('"').strip("'") for tok in rhs.strip(']').lstrip('[').split(',')]
+    out = []
+    for tok in items:
+        for cast in (int, float):
+            try:
+                out.append(cast(tok))
+                break
+            except ValueError:
+                continue
+        else:
+            out.append(tok)
+    return out
+
+
+def extract_dict(line):
+    """``data.parameters['name'] = [...]`` -> ``(name, list)`` (``MCEvidence.py:1188-1193``)."""
+    lhs = line.split('=')[0].strip()
+    name = lhs.split('[')[-1].strip(']').strip('"').strip("'")
+    return name, extract_array(line)
+
+
+def query_yes_no(question, default='yes'):
+    """Interactive yes/no prompt (``MCEvidence.py:1275-1309``): True for yes, False for no; an empty answer takes
+    ``default`` ('yes', 'no' or None = an answer is required)."""
+    answers = {'yes': True, 'y': True, 'ye': True, 'no': False, 'n': False}
+    prompts = {None: ' [y/n] ', 'yes': ' [Y/n] ', 'no': ' [y/N] '}
+    if default not in prompts:
+        raise ValueError("invalid default answer: '%s'" % default)
+    while True:
+        print(question + prompts[default], end='')
+        choice = input().lower()
+        if default is not None and choice == '':
+            return answers[default]
+        if choice in answers:
+            return answers[choice]
+        print("Please respond with 'yes' or 'no' (or 'y' or 'n').")
+
+
 def params_info(fname, cosmo=False, volumes={}):
     """Names, ranges and prior volume of the varied parameters (``MCEvidence.py:1204-1272``).
 

@@ -67,7 +67,8 @@ def test_cli_flags_unchanged_plus_aliases():
 
 def test_module_surface():
     for name in ('MCEvidence', 'MCSamples', 'SamplesMIXIN', 'data_set', 'params_info', 'get_prior_volume',
-                 'iscosmo_param', 'cosmo_params_list', '__version__'):
+                 'iscosmo_param', 'cosmo_params_list', '__version__', 'extract_array', 'extract_dict', 'query_yes_no',
+                 'LoggingHandler', 'use_getdist'):
         assert hasattr(M, name)
     import inspect
     sig = inspect.signature(M.MCEvidence.__init__)

@@ -211,3 +211,40 @@ def test_command_line_matches_live_reference(ref, oracle_ctx, tmp_path, seed, mo
     capsys.readouterr()
     assert got.shape == want.shape
     assert np.abs(got - want).max() < 1e-8
+
+
+def test_module_helpers_match_live_reference(ref, monkeypatch, capsys):
+    """Module-level helpers a user of the reference may import: extract_array / extract_dict on MontePython lines,
+    query_yes_no on scripted answers, and the public surface of the module and its classes."""
+    import io
+    lines = ["data.parameters['omega_b'] = [2.2377, 1.5, None, 0.015, 0.01, 'cosmo']",
+             'data.parameters["A_cib_217"]=[ 61, 0, 200, 7, 1, "nuisance" ]',
+             "data.parameters['H0']          = [1, None, None, 0, 1, 'derived']",
+             "data.cosmo_arguments['k_pivot'] = 0.05",
+             'x = [1e-3, -4, +5.5, text, 7.]']
+    for ln in lines:
+        assert M.extract_array(ln) == ref.extract_array(ln)
+        assert M.extract_dict(ln) == ref.extract_dict(ln)
+    for script, default in (('\n', 'yes'), ('\n', 'no'), ('y\n', None), ('maybe\nNO\n', 'yes'), ('\nye\n', None)):
+        monkeypatch.setattr(sys, 'stdin', io.StringIO(script))
+        want = ref.query_yes_no('Proceed?', default)
+        monkeypatch.setattr(sys, 'stdin', io.StringIO(script))
+        assert M.query_yes_no('Proceed?', default) is want
+    with pytest.raises(ValueError):
+        M.query_yes_no('Proceed?', 'perhaps')
+    capsys.readouterr()
+
+    def public(obj):
+        return {n for n in dir(obj) if not n.startswith('_')}
+    import types
+    own = set()       # what the reference module defines itself (not what it imports)
+    for n in public(ref):
+        v = getattr(ref, n)
+        if isinstance(v, types.ModuleType) or n == 'glob':     # 'glob' is this file's sorted-glob shim
+            continue
+        if getattr(v, '__module__', ref.__name__) == ref.__name__:
+            own.add(n)
+    missing = {n for n in own if not hasattr(M, n)}
+    assert not missing, missing
+    for cls in ('MCEvidence', 'MCSamples', 'SamplesMIXIN', 'data_set', 'LoggingHandler'):
+        assert not public(getattr(ref, cls)) - public(getattr(M, cls)), cls
