@@ -248,3 +248,66 @@ def test_module_helpers_match_live_reference(ref, monkeypatch, capsys):
     assert not missing, missing
     for cls in ('MCEvidence', 'MCSamples', 'SamplesMIXIN', 'data_set', 'LoggingHandler'):
         assert not public(getattr(ref, cls)) - public(getattr(M, cls)), cls
+
+
+def _same(a, b):
+    if isinstance(a, (tuple, list)):
+        return isinstance(b, (tuple, list)) and len(a) == len(b) and all(_same(x, y) for x, y in zip(a, b))
+    if isinstance(a, dict):
+        return isinstance(b, dict) and set(a) == set(b) and all(_same(a[k], b[k]) for k in a)
+    if a is None or b is None:
+        return a is None and b is None
+    a, b = np.asarray(a), np.asarray(b)
+    return a.shape == b.shape and np.allclose(a, b, rtol=1e-12, atol=0, equal_nan=True)
+
+
+@pytest.mark.filterwarnings('ignore::DeprecationWarning')
+@pytest.mark.parametrize('seed', range(6))
+def test_public_methods_match_live_reference(ref, oracle_ctx, seed):
+    """Methods a user may call directly on the two classes (not only through evidence()): containers, burn-in,
+    the three thinning primitives and their dispatcher, importance sampling, covariance, diagonalisation, batch
+    ranges and the summary table."""
+    rng = np.random.default_rng(300 + seed)
+    integer_weights = bool(seed % 2)
+    chains = [gaussian_chain(int(rng.integers(400, 900)), 4, seed=40 * seed + i, cov_seed=seed, integer_weights=integer_weights,
+                             inflate=1.0 if integer_weights else 1.2)[0] for i in range(2)]
+    np.random.seed(seed)
+    r = ref.MCSamples([c.copy() for c in chains])
+    np.random.seed(seed)
+    o = M.MCSamples([c.copy() for c in chains])
+    assert _same(r.get_shape(), o.get_shape())
+    assert _same(r.arrays(), o.arrays()) and _same(r.all_sample_arrays(), o.all_sample_arrays())
+    w = chains[0][:, 0].copy()
+    for unit in (2, 3, 7):
+        assert _same(r.weighted_thin(unit, weights=w.copy()), o.weighted_thin(unit, weights=w.copy()))
+        assert _same(r.get_thin_index(unit, w.copy()), o.get_thin_index(unit, w.copy()))
+        if integer_weights:
+            assert _same(r.thin_indices(unit, weights=w.copy()), o.thin_indices(unit, weights=w.copy()))
+    for frac in (0.2, 0.7):
+        np.random.seed(seed + 1)
+        a = r.poisson_thin(frac, weights=w.copy())
+        np.random.seed(seed + 1)
+        assert _same(a, o.poisson_thin(frac, weights=w.copy()))
+    for burn in (0.25, 37):
+        assert _same(r.removeBurn(burn, chain=chains[1].copy()), o.removeBurn(burn, chain=chains[1].copy()))
+    assert _same(r.thin(nthin=3, chain=chains[0].copy()), o.thin(nthin=3, chain=chains[0].copy()))
+    def extra_neg_loglike(samples):          # an additional Gaussian constraint on the first parameter
+        return 0.5 * ((samples[:, 0] - 0.3) / 0.8) ** 2
+    r.importance_sample(extra_neg_loglike, name='s1')
+    o.importance_sample(extra_neg_loglike, name='s1')
+    assert _same(r.data['s1'].adjusted_weights, o.data['s1'].adjusted_weights)
+    assert _same(r.data['s1'].weights, o.data['s1'].weights)
+
+    np.random.seed(seed)
+    rm = ref.MCEvidence([c.copy() for c in chains], verbose=0, kmax=3, nbatch=2, brange=[2.0, 2.5], bscale='logpower')
+    np.random.seed(seed)
+    om = M.MCEvidence([c.copy() for c in chains], verbose=0, kmax=3, nbatch=2, brange=[2.0, 2.5], bscale='logpower')
+    assert _same(rm.get_batch_range(), om.get_batch_range())
+    s = rm.gd.data['s1'].samples
+    rc, oc = rm.get_covariance(s=s.copy()), om.get_covariance(s=s.copy())
+    assert set(rc) == set(oc) and rc['posdef'] == oc['posdef']
+    assert _same(rc['cov'], oc['cov']) and _same(rc['eVal'], oc['eVal']) and np.isclose(rc['J'], oc['J'], rtol=1e-12)
+    assert _same(np.abs(rc['eVec']), np.abs(oc['eVec']))                             # eigenvectors up to sign
+    rd, od = rm.diagonalise_chain(s.copy(), rc['eVec'], rc['eVal']), om.diagonalise_chain(s.copy(), rc['eVec'], rc['eVal'])
+    assert _same(rd, od)
+    assert _same(rm.get_samples(3, 100, rand=False), om.get_samples(3, 100, rand=False))
