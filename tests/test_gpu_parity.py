@@ -293,9 +293,6 @@ def test_golden_reference_outputs(ctx, golden, tmp_path):
     """End to end through the drop-in class against the frozen outputs of the unmodified reference."""
     import MCEvidence as M
     g = golden
-    if g.name in ('auto_d4_file_int_thin', 'auto_d4_file_weighted_thin') and os.environ.get('MCE_TEST_NEW_GOLDEN') != '1':
-        pytest.skip('fixture added after the last GPU session of round 1 (CPU-verified against the oracle context); '
-                    'enable with MCE_TEST_NEW_GOLDEN=1')
     np.random.seed(g.np_seed)
     mce = M.MCEvidence(g.method(tmp_path), verbose=0, **g.ctor)
     mle = mce.evidence(**g.ev)
