@@ -45,7 +45,7 @@ FP32_PEAK_THEORETICAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.4: SMs x la
 # dram__bytes_read.sum + dram__bytes_write.sum of one K2 launch from the ncu --set full capture of this command
 # (profiles/r01_filter_ncu_raw_final.csv: 148.7 MB read + 31.2 MB written; algorithmic: 44 MB tiles + 80 MB
 # queries + ~24 MB candidate lists -- the reference set is streamed from L2, not from HBM)
-NCU_DRAM_BYTES_PER_LAUNCH = {('cfg2', 1): 179.9e6}
+NCU_DRAM_BYTES_PER_LAUNCH = {('cfg2', 1, False): 179.9e6}   # (workload, gpus, tcgen05 engine?)
 METRIC = 'knn_pair_dists_per_s'
 UNIT = 'pair-dists/s'
 
@@ -131,75 +131,134 @@ def host_info():
             'scipy': scipy.__version__}
 
 
-def cpu_port_once(wl, n_s):
-    """One run of the oracle port of the reference path (sklearn, n_jobs=-1, scalar volume loop as in
-    MCEvidence.py:1108-1110) on the first n_s rows of the workload.  Returns (seconds, logE)."""
+def config_for(name, world):
+    """The `config` object of a workload: identical in both arms (ours / --impl reference)."""
+    n, d, kmax, cross, desc = WORKLOADS[name]
+    return {'workload': desc, 'n': n, 'n_ref': n, 'ndim': d, 'kmax': kmax, 'mode': 'cross' if cross else 'auto',
+            'parallelism': 'our arm: query rows sharded over %d GPU(s), reference set replicated; reference arm: '
+                           'sklearn n_jobs=-1 on the host cores of rank 0' % world,
+            'l2': 'our arm: 512 MiB memset between timed steps (not timed); working set > L2'}
+
+
+def cpu_reference_once(wl, n_s):
+    """One run of the reference's own CPU path on the first n_s rows of the workload: the UNMODIFIED
+    MCEvidence(...).evidence(nproc=-1) staged under oracle/_ref (oracle/ref_loader.py) when it travelled to this
+    box, else the oracle port (numpy + sklearn called as MCEvidence.py:1033-1131 does).  Returns (seconds, logE, kind)."""
+    from oracle import ref_loader
+    d, kmax = wl['d'], wl['kmax']
+    if ref_loader.available():
+        import logging
+        R = ref_loader.load()
+        parts = [np.column_stack((wl['w'][:n_s], -wl['logl'][:n_s], wl['s1'][:n_s]))]
+        if wl['cross']:      # the reference splits one chain at random into s1 / s2 (MCEvidence.py:221-249)
+            parts.append(np.column_stack((wl['w'][:n_s], -wl['logl'][:n_s], wl['s2'][:n_s])))
+        chain = np.concatenate(parts)
+        logging.disable(logging.CRITICAL)
+        try:
+            np.random.seed(0)
+            t = time.perf_counter()
+            mle = R.MCEvidence([chain], kmax=kmax, ndim=d, split=wl['cross'], verbose=0).evidence(nproc=-1)
+            dt = time.perf_counter() - t
+        finally:
+            logging.disable(logging.NOTSET)
+        return dt, np.asarray(mle), 'reference'
     from oracle import mce_oracle as O
-    s1, logl, w = wl['s1'][:n_s], wl['logl'][:n_s], wl['w'][:n_s]
     s2 = wl['s2'][:n_s] if wl['cross'] else None
     t = time.perf_counter()
-    mle = O.evidence(s1, logl, w, wl['d'], wl['kmax'], s2=s2, knn='sklearn', n_jobs=-1, scalar_loop=True)
-    return time.perf_counter() - t, mle
+    mle = O.evidence(wl['s1'][:n_s], wl['logl'][:n_s], wl['w'][:n_s], d, kmax, s2=s2, knn='sklearn', n_jobs=-1,
+                     scalar_loop=True)
+    return time.perf_counter() - t, mle, 'port'
 
 
-def pick_cpu_sample(wl, target_s, n_full):
-    """Calibrate on a small sample, then size the sample for ~target_s seconds of CPU work."""
+def cpu_plan(wl, target_s, n_full):
+    """Calibrate on a small sample and size the per-step sample for ~target_s seconds of CPU work (full size when
+    target_s <= 0).  Returns (n_sample, calibration seconds)."""
+    if target_s <= 0:
+        return n_full, 0.0
     n0 = min(20000, n_full)
-    t0, _ = cpu_port_once(wl, n0)
-    expo = 1.3 if wl['d'] <= 15 else 2.0          # kd_tree ~N^1.3 (SURVEY section 6), brute N^2
-    n_s = int(n0 * (target_s / max(t0, 1e-3)) ** (1.0 / expo))
-    return int(max(n0, min(n_full, n_s))), expo
+    cpu_reference_once(wl, min(4000, n_full))                 # thread pools, imports
+    t0, _, _ = cpu_reference_once(wl, n0)
+    guess = 1.3 if wl['d'] <= 15 else 2.0                     # only to size the sample; the reported exponent is fitted
+    n_s = int(n0 * (target_s / max(t0, 1e-3)) ** (1.0 / guess))
+    return int(max(n0, min(n_full, n_s))), t0
+
+
+def cpu_extrapolate(wl, n_s, t_s, n_full):
+    """Seconds per logE at the full size from the measured sample: t_full = t_s (n_full / n_s)^p with p fitted IN
+    THIS RUN from a second timing at n_s / 2 (kd_tree is ~N^1.3, brute N^2)."""
+    if n_s >= n_full:
+        return t_s, None, None
+    n_h = max(2000, n_s // 2)
+    t_h = min(cpu_reference_once(wl, n_h)[0] for _ in range(2))
+    p_fit = math.log(t_s / t_h) / math.log(n_s / n_h)
+    # The local slope at small N overstates the cost of the kd-tree at large N (SURVEY section 6 measured N^1.3 between
+    # 25k and 400k rows), which would flatter the GPU/CPU ratio: use the smaller of the fitted slope and that law
+    # (N^2 for the brute-force branch, ndim > 15).  Both are reported.
+    ceiling = 1.3 if wl['d'] <= 15 else 2.0
+    p = float(min(ceiling, max(1.0, p_fit)))
+    return t_s * (n_full / n_s) ** p, p, (n_h, t_h, float(p_fit))
 
 
 def cpu_baseline(wl, target_s=20.0):
     n_full = len(wl['s1'])
-    n_s, expo = pick_cpu_sample(wl, target_s, n_full)
-    t, _ = cpu_port_once(wl, n_s)
+    n_s, _ = cpu_plan(wl, target_s, n_full)
+    t, _, kind = cpu_reference_once(wl, n_s)
+    t_full, p, half = cpu_extrapolate(wl, n_s, t, n_full)
     hi = host_info()
     algo = 'kd_tree' if wl['d'] <= 15 else 'brute'
-    val = float(n_s) * float(n_s) / t
-    return {'value': val, 'unit': UNIT, 'cores': hi['cores'], 'kind': 'port',
-            'sample': 'first %d of %d rows of the same chain, whole evidence() port, sklearn %s (%s), n_jobs=-1: %.2f s; '
-                      'pair-equivalents = N_s^2/t. Cost grows ~N^%.1f, so at full N the CPU figure would be '
-                      '~(N/N_s)^%.1f = %.1fx higher (%.0f s per logE extrapolated)' % (
-                          n_s, n_full, hi['sklearn'], algo, t, expo, 2 - expo, (n_full / n_s) ** (2 - expo),
-                          t * (n_full / n_s) ** expo),
-            'seconds': t, 'n_sample': n_s, 'cpu_model': hi['cpu_model'],
-            's_per_logE_full_extrapolated': t * (n_full / n_s) ** expo}
+    n_ref = len(wl['s2']) if wl['cross'] else n_full
+    sample = ('%s MCEvidence(...).evidence(nproc=-1), sklearn %s (%s), %d cores: first %d of %d rows of the same chain in '
+              '%.2f s' % ('unmodified reference (oracle/_ref)' if kind == 'reference' else 'oracle port of', hi['sklearn'],
+                          algo, hi['cores'], n_s, n_full, t))
+    if p is not None:
+        sample += ('; %d rows in %.2f s -> slope N^%.2f fitted in this run, N^%.2f used (capped at the large-N law); value = '
+                   'N_full^2 / t_full with t_full = %.1f s EXTRAPOLATED' % (half[0], half[1], half[2], p, t_full))
+    return {'value': float(n_full) * float(n_ref) / t_full, 'unit': UNIT, 'cores': hi['cores'], 'kind': kind,
+            'sample': sample, 'seconds': t, 'n_sample': n_s, 'cpu_model': hi['cpu_model'], 'extrapolated': p is not None,
+            'fit_exponent': half[2] if half else None, 'used_exponent': p, 's_per_logE_full': t_full}
 
 
 # ---------------------------------------------------------------------------------------------
 def run_reference_arm(args, rank, world):
-    """--impl reference: the reference's CPU path (oracle port: numpy + sklearn exactly as
-    MCEvidence.py:1033-1131 calls them) on the host cores, rank 0 only."""
+    """--impl reference: the reference's own CPU path on the host cores of rank 0 -- the unmodified
+    MCEvidence.evidence() staged under oracle/_ref (kind "reference"), else the oracle port.  Each step is a bounded
+    sample of the workload; `value` is the like-for-like figure for the FULL configuration, pair-distances of the
+    full problem / seconds per logE at full size, extrapolated with an exponent fitted in this run
+    (--cpu-seconds 0 runs the full size instead: minutes per step)."""
     if rank != 0:
         return 0
     wl = make_workload(args.workload)
     n_full = len(wl['s1'])
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    n_s, expo = pick_cpu_sample(wl, min(25.0, budget, args.cpu_seconds if args.cpu_seconds > 0 else 25.0), n_full)
-    for _ in range(args.warmup):
-        cpu_port_once(wl, n_s)
-    times = []
+    n_ref = len(wl['s2']) if wl['cross'] else n_full
+    budget = 200.0 / max(1, args.steps + args.warmup + 1)
+    target = 0.0 if args.cpu_seconds <= 0 else min(25.0, budget, args.cpu_seconds)
+    n_s, _ = cpu_plan(wl, target, n_full)
+    for _ in range(args.warmup if n_s < n_full else 0):
+        cpu_reference_once(wl, n_s)
+    times, kind = [], 'port'
     for _ in range(args.steps):
-        t, mle = cpu_port_once(wl, n_s)
+        t, mle, kind = cpu_reference_once(wl, n_s)
         times.append(t)
-    tt = float(np.sum(times))
+    t_step = float(np.mean(times))
+    t_full, p, half = cpu_extrapolate(wl, n_s, t_step, n_full)
     hi = host_info()
-    val = args.steps * float(n_s) * float(n_s) / tt
-    sample = ('first %d of %d rows per step, oracle port of MCEvidence.evidence() (sklearn %s, %s, n_jobs=-1, %d cores); '
-              'cost ~N^%.1f so full-size pair-equivalents/s would be ~%.1fx higher' % (
-                  n_s, n_full, hi['sklearn'], 'kd_tree' if wl['d'] <= 15 else 'brute', hi['cores'], expo,
-                  (n_full / n_s) ** (2 - expo)))
+    val = float(n_full) * float(n_ref) / t_full
+    algo = 'kd_tree' if wl['d'] <= 15 else 'brute'
+    sample = ('%s MCEvidence(...).evidence(nproc=-1), sklearn %s (%s), %d cores; each step = first %d of %d rows' % (
+        'unmodified reference (oracle/_ref)' if kind == 'reference' else 'oracle port of', hi['sklearn'], algo, hi['cores'],
+        n_s, n_full))
+    if p is not None:
+        sample += ('; %.2f s per step, %d rows in %.2f s -> slope N^%.2f fitted in this run, N^%.2f used (capped at the large-N '
+                   'law); value is for the full configuration: N_full^2 / t_full, t_full = %.1f s EXTRAPOLATED' % (
+                       t_step, half[0], half[1], half[2], p, t_full))
     line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': 1e3 * tt / args.steps, 'higher_is_better': True, 'scaling': 'strong',
-            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': wl['desc'], 'sample_rows': n_s},
-            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': hi['cores'], 'kind': 'port', 'sample': sample,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * t_step, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': config_for(args.workload, max(1, args.gpus)),
+            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': hi['cores'], 'kind': kind, 'sample': sample,
                              'cpu_model': hi['cpu_model']},
             'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-            's_per_logE_full_extrapolated': (tt / args.steps) * (n_full / n_s) ** expo,
-            'gpu_launches': 0}
+            'extrapolated': p is not None, 'fit_exponent': half[2] if half else None, 'used_exponent': p, 'sample_rows': n_s, 's_per_logE': t_full,
+            's_per_logE_sample': t_step, 'logE_sample': [float(x) for x in np.ravel(mle)], 'gpu_launches': 0}
     print(json.dumps(line), flush=True)
     return 0
 
@@ -229,7 +288,8 @@ def main():
                          "K2-TC); not given = the library default or MCE_FILTER_ENGINE")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-seconds', type=float, default=20.0,
-                    help='target seconds of CPU work for the cpu_baseline sample / per step of the reference arm')
+                    help='target seconds of CPU work for the cpu_baseline sample / per step of the reference arm; '
+                         '0 = the full configuration (minutes per step at cfg2)')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-API leg (long scaling runs only)')
     ap.add_argument('--allow-short-warmup', action='store_true',
                     help='do not raise --warmup to 3 (minutes-long steps of the cfg5 scaling run only)')
@@ -376,33 +436,36 @@ def main():
         pairs_launch = float(hi - lo) * float(n_ref)                    # units one K2 launch processes on rank 0
         t_k2 = float(np.mean(ms_filter)) * 1e-3
         achieved = 3.0 * d * pairs_launch / t_k2 / 1e12                 # algorithmic: 3d FLOP per pair (sub, mul, add)
-        roofline = {'bound': 'fp32_fma', 'achieved': achieved, 'peak': fma_peak, 'unit': 'TFLOP/s',
-                    'frac': achieved / fma_peak, 'traffic': NCU_DRAM_BYTES_PER_LAUNCH.get((args.workload, world)),
+        exec_fma = 2.0 * d * pairs_launch / t_k2 / 1e12               # executed: d FMA per pair (score form)
+        roofline = {'bound': 'fp32_fma', 'achieved': achieved, 'peak': FP32_PEAK_THEORETICAL_TFLOPS, 'unit': 'TFLOP/s',
+                    'frac': achieved / FP32_PEAK_THEORETICAL_TFLOPS,
+                    'traffic': NCU_DRAM_BYTES_PER_LAUNCH.get((args.workload, world, stats['filter_mode'] == 16)),
                     'kernel': 'knn_filter_kernel<D=%d,TQ=%d,TR=%d,packed=%d,mode=%d>' % (
                         d, stats['filter_tq'], stats['filter_tr'], stats['filter_packed'], stats['filter_mode']),
                     'ms_per_launch': 1e3 * t_k2, 'share_of_step': float(np.sum(ms_filter)) / t_ms if world == 1 else None,
-                    'peak_source': 'FMA microbenchmark in this run (mce_fma_peak): ffma %.1f, ffma2 %.1f TFLOP/s at 2 FLOP per '
-                                   'lane-FMA; theoretical %.1f' % (peak['ffma'], peak['ffma2'], FP32_PEAK_THEORETICAL_TFLOPS),
-                    'frac_theoretical': achieved / FP32_PEAK_THEORETICAL_TFLOPS,
-                    'fma_pipe_frac': (2.0 * d * pairs_launch / t_k2 / 1e12) / fma_peak,
-                    'note': 'the filter issues d FMAs per pair (2d executed FLOP) for the 3d algorithmic FLOP of the '
-                            'difference form, so frac can exceed 1; fma_pipe_frac is executed FMA rate / measured FMA peak'}
+                    'peak_source': 'theoretical FP32 FMA peak 148 SMs x 128 lanes x 2 FLOP x 1.965 GHz = %.1f TFLOP/s '
+                                   '(MEASURED_PEAKS.json has no FP32 entry; the FMA microbenchmark of this run, mce_fma_peak, '
+                                   'reads ffma %.1f / ffma2 %.1f)' % (FP32_PEAK_THEORETICAL_TFLOPS, peak['ffma'], peak['ffma2']),
+                    'algorithmic_tflops': achieved, 'executed_fma_tflops': exec_fma,
+                    'fma_pipe_frac': exec_fma / FP32_PEAK_THEORETICAL_TFLOPS,
+                    'note': 'achieved = algorithmic 3d FLOP per pair (sub, mul, add; SURVEY 8d M4); the filter executes d FMA '
+                            '= 2d FLOP per pair, so frac can exceed 1; fma_pipe_frac = executed FMA rate / theoretical peak'}
         if stats['filter_mode'] == 16:
-            # tcgen05 engine: the d FMAs per pair run on the tensor cores as a TF32 MMA of depth K = 8 ceil((d+2)/8)
+            # tcgen05 engine: the d FMAs per pair run on the tensor cores as TF32 MMAs of depth K = 8 ceil((d+2)/8)
             kpad = 8 * ((d + 2 + 7) // 8)
             tf32_peak = _measured_tf32_peak()
             mma = 2.0 * kpad * pairs_launch / t_k2 / 1e12
             roofline.update({'bound': 'tensor', 'achieved': mma, 'peak': tf32_peak[0], 'frac': mma / tf32_peak[0],
                              'kernel': 'knn_filter_tc_kernel<KSTEPS=%d>' % (kpad // 8), 'peak_source': tf32_peak[1],
-                             'algorithmic_tflops': achieved, 'fma_pipe_frac': None, 'frac_theoretical': None, 'traffic': None,
-                             'note': 'achieved = executed TF32 MMA FLOP (2 K per pair, K = %d for ndim %d); the algorithmic 3d '
-                                     'FLOP per pair are in algorithmic_tflops' % (kpad, d)})
+                             'fma_pipe_frac': None, 'executed_fma_tflops': None,
+                             'algorithmic_frac_of_fp32_fma_peak': achieved / FP32_PEAK_THEORETICAL_TFLOPS,
+                             'note': 'achieved = executed TF32 MMA FLOP (2 K per pair, K = %d for ndim %d) against half the '
+                                     'measured bf16 peak; algorithmic_tflops = 3d FLOP per pair (SURVEY 8d M4), beside it as '
+                                     'a fraction of the theoretical FP32 FMA peak the CUDA-core filter is bounded by' % (kpad, d)})
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': t_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
                 'dtype': 'f32 filter, f64 re-rank/reduce', 'data': 'synthetic',
-                'config': {'workload': m['desc'], 'n': n, 'n_ref': n_ref, 'ndim': d, 'kmax': kmax, 'mode': 'cross' if cross else 'auto',
-                           'parallelism': 'query rows sharded over %d GPU(s), reference set replicated' % world,
-                           'l2': '512 MiB memset between timed steps (not timed); working set > L2'},
+                'config': config_for(args.workload, world),
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                         's_per_logE': None if args.no_e2e else te / args.steps},
                 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline,

@@ -93,7 +93,7 @@ struct mce_ctx {
     int opt_tq = -1, opt_tr = -1, opt_packed = -1, opt_chunks = -1, opt_margin = -1, opt_sync = -1, opt_tail = -1;
     // tensor-core engine of the filter (opt-in): 0 = FFMA filter, 1 = tcgen05; check = also evaluate every pair
     // exactly and record the worst |coarse - exact| / e; slack = percent of the default error allowance
-    int opt_engine = 0, opt_tc_check = 0, opt_tc_swap = 0, opt_tc_slack = 100, opt_tc_stages = -1, opt_tc_perf = 0;
+    int opt_engine = 0, opt_tc_check = 0, opt_tc_swap = 0, opt_tc_slack = 100, opt_tc_stages = -1, opt_tc_perf = 0, opt_tc_timeline = 0;
     double dbg_tc_ratio = 0.0, dbg_tc_pairs = 0.0;
     std::vector<float> dbg_tc_dump;   // tc_check: coarse scores of unit 0, tile 0 ([256 queries][128 references])
     DevBuf xq, xr, logl, w, yr, yq, tiles, tc_tiles, tc_debug, tc_dump, cand_idx, cand_th, dknn, idx, flagged, covpart, redpart, scal,
@@ -471,6 +471,13 @@ int run_problem(mce_ctx* c, const Run& r) {
             tp.slack_rr = (float)(scale * 0.5 * (ldexp(1.0, -20) + ldexp(1.0, -14)));
             tp.debug = c->tc_debug.as<unsigned int>();
             tp.dump = nullptr;
+            tp.timeline = nullptr;
+            if (c->opt_tc_timeline && !c->opt_tc_check) {
+                rc = c->tc_dump.ensure((size_t)TC_QUERIES * TC_TILE_REFS * sizeof(float));
+                if (rc) return rc;
+                CU(cudaMemsetAsync(c->tc_dump.p, 0, (size_t)TC_QUERIES * TC_TILE_REFS * sizeof(float), st));
+                tp.timeline = c->tc_dump.as<long long>();   // 1024 tiles x 16 events x 8 bytes = the dump buffer
+            }
             if (c->opt_tc_check) {
                 rc = c->tc_dump.ensure((size_t)TC_QUERIES * TC_TILE_REFS * sizeof(float));
                 if (rc) return rc;
@@ -578,6 +585,10 @@ int run_problem(mce_ctx* c, const Run& r) {
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
 
+    if (use_tc && c->opt_tc_timeline && !c->opt_tc_check && !exact_only) {
+        c->dbg_tc_dump.resize((size_t)TC_QUERIES * TC_TILE_REFS);
+        CU(cudaMemcpy(c->dbg_tc_dump.data(), c->tc_dump.p, c->dbg_tc_dump.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    }
     if (use_tc && c->opt_tc_check && !exact_only) {
         unsigned int dbg[2] = {0, 0};
         CU(cudaMemcpy(dbg, c->tc_debug.p, sizeof(dbg), cudaMemcpyDeviceToHost));
@@ -730,6 +741,7 @@ int mce_ctx_set_option(mce_ctx* c, const char* name, int value) {
     } else if (!strcmp(name, "tc_check")) c->opt_tc_check = value != 0;
     else if (!strcmp(name, "tc_swap_offsets")) c->opt_tc_swap = value & 3;   // bit 0: exchange the offsets, bit 1: version field 0
     else if (!strcmp(name, "tc_stages")) c->opt_tc_stages = value;
+    else if (!strcmp(name, "tc_timeline")) c->opt_tc_timeline = value != 0;
     else if (!strcmp(name, "tc_perf_mode")) c->opt_tc_perf = (value == 1 || value == 2) ? value : 0;
     else if (!strcmp(name, "tc_slack_percent")) {
         if (value < 1) return fail(MCE_ERR_ARG, "tc_slack_percent must be positive");

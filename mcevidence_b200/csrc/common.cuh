@@ -110,6 +110,7 @@ struct TcFilterParams {
     const unsigned int* rmax_bits;    // max |y| over the references (written by K1)
     float slack_qr, slack_rr;         // coarse-score error bound e = slack_qr |q| Rmax + slack_rr Rmax^2
     unsigned int* debug;              // CHECK builds: [0] max over pairs of |coarse - exact| / e as float bits, [1] pairs checked (mod 2^32)
+    long long* timeline;              // timing diagnostics: clock64() of the hand-over points of CTA 0's first tiles, or null
     float* dump;                      // CHECK builds: coarse scores of unit 0, tile 0: [TC_QUERIES][TC_TILE_REFS] (may be null)
     int stages;                       // shared-memory ring depth
     int swap_offsets;                 // debug bits: 1 = exchange the leading/stride byte offsets of the descriptors, 2 = version field 0

@@ -195,7 +195,17 @@ __device__ __forceinline__ void tc_process(const uint32_t (&v)[32], int col0, ui
     }
 }
 
-template <int KSTEPS, bool CHECK>
+// TL builds record clock64() of the hand-over points of the first 1024 tiles of CTA 0 into tp.timeline ([tile][16]):
+// MMA warp 0 tile landed, 1/3 accumulator free (query block 0/1), 2/4 MMAs + commit issued; epilogue warp 0 (block 0)
+// 5 accumulator full, 6 accumulator released, 7 tile done; epilogue warp 4 (block 1) 8, 9, 10; producer 11 slot free
+#define TC_MARK(IT, SLOT)                                                                            \
+    do {                                                                                             \
+        if constexpr (TL) {                                                                          \
+            if (blockIdx.x == 0 && (IT) < 1024 && lane == 0) tp.timeline[(IT) * 16 + (SLOT)] = clock64(); \
+        }                                                                                            \
+    } while (0)
+
+template <int KSTEPS, bool CHECK, bool TL>
 __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFilterParams tp) {
     constexpr int K = KSTEPS * 8;
     constexpr uint32_t TILE_BYTES = (uint32_t)K * TC_TILE_REFS * 4;   // K/4 chunks of 2 KB
@@ -316,6 +326,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
                     const uint32_t fb = smem_u32(&bar_free[slot]);
                     tc_wait(fb, (uint32_t)(round - 1) & 1u);
                 }
+                if constexpr (TL) {
+                    if (blockIdx.x == 0 && n < 1024) tp.timeline[n * 16 + 11] = clock64();
+                }
                 const uint32_t bar = smem_u32(&bar_full[slot]);
                 mbar_arrive_expect_tx(bar, TILE_BYTES);
                 tma_bulk_g2s(smem_u32(ring) + (uint32_t)slot * TILE_BYTES, gt + (size_t)n * TILE_BYTES, TILE_BYTES, bar);
@@ -338,12 +351,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
                 const uint32_t fb = smem_u32(&bar_full[slot]);
                 tc_wait(fb, (uint32_t)round & 1u);
             }
+            TC_MARK(it, 0);
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb) {
                 if (it >= 2) {   // the query block's epilogue warps have drained this buffer (tile it - 2)
                     const uint32_t ab = smem_u32(&bar_acc_free[2 * buf + mb]);
                     tc_wait(ab, (uint32_t)((it >> 1) - 1) & 1u);
                 }
+                TC_MARK(it, 1 + 2 * mb);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u + (uint32_t)mb * 128u;
@@ -356,6 +371,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
                     umma_commit(smem_u32(&bar_acc_full[2 * buf + mb]));   // this query block's warps can start
                 }
                 __syncwarp();
+                TC_MARK(it, 2 + 2 * mb);
             }
             __syncwarp();
             if (++slot == NS) {
@@ -375,6 +391,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
             }
             __syncwarp();   // lanes may leave the spin loop at different times
             tc_fence_after();
+            if (quad == 0) TC_MARK(it, 5 + 3 * mb);
             st.full_bar = smem_u32(&bar_full[slot]);
             st.full_parity = (uint32_t)round & 1u;
             st.acquired = false;
@@ -403,6 +420,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bar_acc_free[2 * buf + mb]));
+                if (quad == 0) TC_MARK(it, 6 + 3 * mb);
                 tc_process<CHECK>(vb, 96, tile, ridx0, st);
             } else {
                 if (tp.perf_mode == 2) {   // the four loads alone
@@ -421,10 +439,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bar_acc_free[2 * buf + mb]));
+                if (quad == 0) TC_MARK(it, 6 + 3 * mb);
             }
             // the slow path reads the operand tile: release the ring slot only now
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_free[slot]));
+            if (quad == 0) TC_MARK(it, 7 + 3 * mb);
             if (++slot == NS) {
                 slot = 0;
                 ++round;
@@ -461,12 +481,20 @@ size_t tc_fixed_smem(int K, int list_len) {
 
 template <int KSTEPS>
 int tc_launch_k(const TcFilterParams& tp, unsigned grid, size_t smem, cudaStream_t st) {
+    if constexpr (KSTEPS == 2) {
+        if (tp.timeline) {   // timing diagnostics (ndim 7..14 only)
+            auto kern = knn_filter_tc_kernel<KSTEPS, false, true>;
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+            kern<<<grid, TC_THREADS, smem, st>>>(tp);
+            return cudaGetLastError() == cudaSuccess ? 0 : -1;
+        }
+    }
     if (tp.check) {
-        auto kern = knn_filter_tc_kernel<KSTEPS, true>;
+        auto kern = knn_filter_tc_kernel<KSTEPS, true, false>;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
         kern<<<grid, TC_THREADS, smem, st>>>(tp);
     } else {
-        auto kern = knn_filter_tc_kernel<KSTEPS, false>;
+        auto kern = knn_filter_tc_kernel<KSTEPS, false, false>;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
         kern<<<grid, TC_THREADS, smem, st>>>(tp);
     }
