@@ -283,9 +283,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
-    ap.add_argument('--filter-engine', default=None, choices=['ffma', 'tc'],
-                    help="K2 engine: 'ffma' (FP32 FMA pipe, the library default) or 'tc' (opt-in tcgen05 engine, see DESIGN.md "
-                         "K2-TC); not given = the library default or MCE_FILTER_ENGINE")
+    ap.add_argument('--filter-engine', default=None, choices=['ffma', 'tc', 'auto'],
+                    help="K2 engine: 'ffma' (FP32 FMA pipe), 'tc' (tcgen05 tensor-core filter) or 'auto' (chosen per problem, "
+                         "the library default); not given = the library default or MCE_FILTER_ENGINE")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-seconds', type=float, default=20.0,
                     help='target seconds of CPU work for the cpu_baseline sample / per step of the reference arm; '
@@ -321,7 +321,7 @@ def main():
     stream = torch.cuda.current_stream(device)
     ctx.set_stream(stream.cuda_stream)
     if args.filter_engine is not None:
-        ctx.set_option('filter_engine', 1 if args.filter_engine == 'tc' else 0)
+        ctx.set_option('filter_engine', {'ffma': 0, 'tc': 1, 'auto': 2}[args.filter_engine])
 
     wl = make_workload(args.workload) if rank == 0 else None
     meta = [None]

@@ -128,15 +128,17 @@ void mce_ctx_destroy(mce_ctx *ctx);
 int  mce_ctx_set_stream(mce_ctx *ctx, void *cuda_stream);
 /* Tuning knobs: "filter_tq", "filter_tr", "filter_packed", "filter_sync" (kernel mode 0/1/2), "ref_chunks"
    (uniform split of the reference set), "list_margin". -1 = automatic.
-   "filter_engine": 0 = FP32 FFMA filter (default), 2 = choose per problem (tcgen05 for ndim >= 4 and at least
-   2e8 pairs), 1 = tcgen05 tensor-core filter (TF32 coarse scores in TMEM,
-   exact FP32 evaluation of the columns that pass; same candidates contract, stats.filter_mode reports 16); the
-   environment variable MCE_FILTER_ENGINE=1 (or 2) sets the initial value of every new context.
-   Diagnostics of engine 1: "tc_check" (1: also evaluate every pair exactly and record the worst
+   "filter_engine": 2 = chosen per problem (default: the tcgen05 filter for ndim >= 4 and at least ~6e8 pairs, 2e8
+   from ndim 10 on -- where it was measured faster on B200 -- otherwise the FP32 FFMA filter), 0 = FFMA filter,
+   1 = tcgen05 tensor-core filter (TF32 coarse scores in TMEM, exact FP32 evaluation of the columns that pass; same
+   candidates contract, stats.filter_mode reports 16); the environment variable MCE_FILTER_ENGINE=0/1/2 sets the
+   initial value of every new context.
+   Diagnostics of the tcgen05 engine: "tc_check" (1: also evaluate every pair exactly and record the worst
    |coarse - exact| / allowance, read back with mce_ctx_get_debug), "tc_slack_percent" (scales the allowance,
-   default 100), "tc_swap_offsets" (bit 0: exchange the two byte offsets of the shared-memory matrix descriptors, bit 1: descriptor
-   version field 0),
-   "tc_stages" (shared-memory ring depth 2..8, -1 = as many as fit), "tc_perf_mode" (timing experiments whose
+   default 100), "tc_swap_offsets" (bit 0: exchange the two byte offsets of the shared-memory matrix descriptors,
+   bit 1: descriptor version field 0), "tc_stages" (shared-memory ring depth 2..8, -1 = as many as fit),
+   "tc_mma_warps" (1 or 2 warps issuing the MMAs, default 2), "tc_timeline" (ndim 7..14: record the hand-over
+   times of CTA 0's first 1024 tiles, read back as "tc_dump"), "tc_perf_mode" (ndim 7..14, timing experiments whose
    results are garbage: 1 = the epilogue skips the TMEM loads, 2 = loads without the threshold test). */
 int  mce_ctx_set_option(mce_ctx *ctx, const char *name, int value);
 /* Diagnostics of the last call on this context: "tc_check_ratio" (worst |coarse - exact| / allowance seen by a

@@ -91,9 +91,9 @@ struct mce_ctx {
     cudaStream_t stream = nullptr;
     std::mutex mu;
     int opt_tq = -1, opt_tr = -1, opt_packed = -1, opt_chunks = -1, opt_margin = -1, opt_sync = -1, opt_tail = -1;
-    // tensor-core engine of the filter (opt-in): 0 = FFMA filter, 1 = tcgen05; check = also evaluate every pair
-    // exactly and record the worst |coarse - exact| / e; slack = percent of the default error allowance
-    int opt_engine = 0, opt_tc_check = 0, opt_tc_swap = 0, opt_tc_slack = 100, opt_tc_stages = -1, opt_tc_perf = 0, opt_tc_timeline = 0;
+    // engine of the filter: 0 = FFMA filter, 1 = tcgen05, 2 = chosen per problem (default); check = also evaluate every
+    // pair exactly and record the worst |coarse - exact| / e; slack = percent of the default error allowance
+    int opt_engine = 2, opt_tc_check = 0, opt_tc_swap = 0, opt_tc_slack = 100, opt_tc_stages = -1, opt_tc_perf = 0, opt_tc_timeline = 0, opt_tc_mma_warps = 2;
     double dbg_tc_ratio = 0.0, dbg_tc_pairs = 0.0;
     std::vector<float> dbg_tc_dump;   // tc_check: coarse scores of unit 0, tile 0 ([256 queries][128 references])
     DevBuf xq, xr, logl, w, yr, yq, tiles, tc_tiles, tc_debug, tc_dump, cand_idx, cand_th, dknn, idx, flagged, covpart, redpart, scal,
@@ -334,8 +334,10 @@ int run_problem(mce_ctx* c, const Run& r) {
                       &launches);
         yq_base = c->yr.as<double>();
     }
-    // engine 2 = automatic: the tensor-core engine where its coarse stage is selective (ndim >= 4), the problem is
-    // large enough to amortise a 256-query x 128-reference tile per CTA, and its shared-memory footprint fits
+    // engine 2 = automatic (the default): the tcgen05 engine where it was measured faster than the FFMA filter on B200
+    // (profiles/r02_engine_sweep.json): ndim >= 4 and at least ~6e8 pairs (2e8 from ndim 10 on).  Below that the
+    // 256-query x 128-reference tiles of one CTA per SM cannot fill the GPU, and for ndim <= 3 the TF32 allowance
+    // admits too many false candidates.
     bool use_tc = false;
     if ((c->opt_engine == 1 || c->opt_engine == 2) && !(p.flags & MCE_FLAG_EXACT_ONLY)) {
         int q0 = 0, s0 = 0, c0 = 0, st0 = 0;
@@ -344,7 +346,10 @@ int run_problem(mce_ctx* c, const Run& r) {
             if (!fits) return fail(MCE_ERR_ARG, "no tensor-core filter for ndim=%d with %d neighbours", d, K);
             use_tc = true;
         } else {
-            use_tc = fits && d >= 4 && (double)nq * (double)n_ref >= 2e8;
+            // an explicit FFMA tiling option (tests, tuning runs) keeps the FFMA filter
+            const bool ffma_tuned = c->opt_tq > 0 || c->opt_tr > 0 || c->opt_packed >= 0 || c->opt_sync >= 0;
+            const double pairs = (double)nq * (double)n_ref;
+            use_tc = fits && !ffma_tuned && d >= 4 && pairs >= (d >= 10 ? 2e8 : 6e8);
         }
     }
     if (use_tc) {
@@ -488,6 +493,7 @@ int run_problem(mce_ctx* c, const Run& r) {
             tp.swap_offsets = c->opt_tc_swap;
             tp.check = c->opt_tc_check;
             tp.perf_mode = c->opt_tc_perf;
+            tp.mma_warps = c->opt_tc_mma_warps;
             if (launch_tc_filter(tp, st, &launches) != 0)
                 return fail(MCE_ERR_CUDA, "tensor-core filter launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         } else if (launch_filter(fp, cfg, st, &launches) != 0) {
@@ -599,6 +605,13 @@ int run_problem(mce_ctx* c, const Run& r) {
         c->dbg_tc_dump.resize((size_t)TC_QUERIES * TC_TILE_REFS);
         CU(cudaMemcpy(c->dbg_tc_dump.data(), c->tc_dump.p, c->dbg_tc_dump.size() * sizeof(float), cudaMemcpyDeviceToHost));
     }
+    if (use_tc && !exact_only) {
+        unsigned int stuck[4] = {0u, 0u, 0u, 0u};
+        if (tc_read_stuck(stuck, st) != 0) return fail(MCE_ERR_CUDA, "reading the tcgen05 filter's wait record failed");
+        if (stuck[0] != 0u)
+            return fail(MCE_ERR_INTERNAL, "tcgen05 filter: a %s wait made no progress for 0.5 s and gave up (a=0x%x b=0x%x block=%u); "
+                        "results discarded", stuck[0] == 1u ? "barrier" : stuck[0] == 2u ? "queue-full" : "queue-slot", stuck[1], stuck[2], stuck[3]);
+    }
     if (c->hscal->status != 0)
         return fail(MCE_ERR_NOT_POSDEF,
                     "sample covariance of the %d selected parameters is not positive definite "
@@ -686,7 +699,8 @@ int mce_ctx_create(int device, mce_ctx** out) {
     if (!c) return fail(MCE_ERR_NOMEM, "out of host memory");
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    if (const char* eng = getenv("MCE_FILTER_ENGINE")) c->opt_engine = ((eng[0] == '1' || eng[0] == '2') && eng[1] == '\0') ? eng[0] - '0' : 0;
+    if (const char* eng = getenv("MCE_FILTER_ENGINE"))
+        if (eng[0] >= '0' && eng[0] <= '2' && eng[1] == '\0') c->opt_engine = eng[0] - '0';
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMallocHost(reinterpret_cast<void**>(&c->hscal), sizeof(DevScalars)) != cudaSuccess) {
         const char* msg = cudaGetErrorString(cudaGetLastError());
@@ -742,6 +756,7 @@ int mce_ctx_set_option(mce_ctx* c, const char* name, int value) {
     else if (!strcmp(name, "tc_swap_offsets")) c->opt_tc_swap = value & 3;   // bit 0: exchange the offsets, bit 1: version field 0
     else if (!strcmp(name, "tc_stages")) c->opt_tc_stages = value;
     else if (!strcmp(name, "tc_timeline")) c->opt_tc_timeline = value != 0;
+    else if (!strcmp(name, "tc_mma_warps")) c->opt_tc_mma_warps = value == 1 ? 1 : 2;
     else if (!strcmp(name, "tc_perf_mode")) c->opt_tc_perf = (value == 1 || value == 2) ? value : 0;
     else if (!strcmp(name, "tc_slack_percent")) {
         if (value < 1) return fail(MCE_ERR_ARG, "tc_slack_percent must be positive");

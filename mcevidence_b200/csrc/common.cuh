@@ -21,6 +21,7 @@ __host__ __device__ constexpr int tile_refs(int d) { return d <= 10 ? 256 : 128;
 constexpr int FILTER_THREADS = 128;   // threads per filter CTA (4 warps)
 constexpr int FILTER_STAGES = 4;      // TMA ring depth
 constexpr int KCAP = 16;              // == MCE_MAX_NEIGHBOURS
+#define MCE_TC_LIST_MAX 20             // tcgen05 engine: longest candidate list (KCAP + margin <= 4)
 constexpr int MAX_DIM = 64;           // == MCE_MAX_DIM
 
 struct Segment {            // one strided sample array, float64 or float32 (MCE_FLAG_F32_SAMPLES)
@@ -115,6 +116,7 @@ struct TcFilterParams {
     int stages;                       // shared-memory ring depth
     int swap_offsets;                 // debug bits: 1 = exchange the leading/stride byte offsets of the descriptors, 2 = version field 0
     int check;                        // 1: evaluate every pair exactly as well and record the worst ratio in debug[]
+    int mma_warps;                    // 1 or 2 warps issuing the MMAs (2: even / odd tiles)
     int perf_mode;                    // timing experiments only (results are garbage): 1 = epilogue skips the TMEM loads
                                       // (MMA + TMA pipeline alone), 2 = loads without the threshold test
 };
@@ -126,6 +128,8 @@ void launch_tc_image(const double* y64, const float* ffma_tiles, long long n_ref
 // want_stages <= 0: as many ring slots (2..8) as fit the shared-memory budget
 int tc_filter_query(int d, int list_len, int want_stages, int* queries_per_cta, int* smem_bytes, int* ctas_per_sm, int* stages);
 int launch_tc_filter(const TcFilterParams& p, cudaStream_t st, int* launches);
+// {flag, a, b, block} of a barrier wait that gave up (0 flag = none); clears the record
+int tc_read_stuck(unsigned int (&out)[4], cudaStream_t st);
 
 // ---- K3: FP64 re-rank + verification, exact re-scan ---------------------------------------
 struct RerankParams {

@@ -33,10 +33,13 @@ namespace mce {
 
 namespace {
 
-constexpr int TC_EPI_WARPS = 8;
-constexpr int TC_PRODUCER_WARP = 8;
-constexpr int TC_MMA_WARP = 9;
-constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
+constexpr int TC_EPI_WARPS = 16;             // warp w: TMEM lane quadrant w%4, query block (w/4)%2, column half w/8
+constexpr int TC_PRODUCER_WARP = 16;
+constexpr int TC_MMA_WARP = 17;              // issues the MMAs of the even tiles (of every tile with one issuing warp)
+constexpr int TC_MMA_WARP2 = 18;             // issues the MMAs of the odd tiles when tp.mma_warps == 2
+constexpr int TC_SELECT_WARP = 19;           // exact evaluation of the hits, owner of the top-L lists
+constexpr int TC_HALF_COLS = TC_TILE_REFS / 2;   // columns of a tile looked at by one epilogue thread
+constexpr int TC_THREADS = (TC_EPI_WARPS + 4) * 32;
 constexpr int TC_QBLK = 128;                 // UMMA M
 constexpr uint32_t TC_TMEM_COLS = 512;       // 2 accumulator buffers x 2 query blocks x 128 columns
 constexpr uint32_t TC_CHUNK_BYTES = (TC_TILE_REFS / 8) * 128;   // one 16-byte K chunk of all rows of a tile: 2048
@@ -48,123 +51,212 @@ constexpr int TC_SMEM_BUDGET = 200 * 1024;
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_TILE_REFS >> 3) << 17) |
                               ((uint32_t)(TC_QBLK >> 4) << 24);
 
-// maxima of 32 scores in three levels of FMNMX(3), 17 instructions: b[j] covers columns 9j .. 9j+8 (b[3]: 27..31)
-__device__ __forceinline__ float max32(const uint32_t (&v)[32], float (&b)[4]) {
+// maximum of 32 scores in three levels of FMNMX(3), 17 instructions
+__device__ __forceinline__ float max32(const uint32_t* v) {
     float a[11];
 #pragma unroll
     for (int j = 0; j < 10; ++j)
         a[j] = max3(__uint_as_float(v[3 * j]), __uint_as_float(v[3 * j + 1]), __uint_as_float(v[3 * j + 2]));
     a[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
-    b[0] = max3(a[0], a[1], a[2]);
-    b[1] = max3(a[3], a[4], a[5]);
-    b[2] = max3(a[6], a[7], a[8]);
-    b[3] = fmaxf(a[9], a[10]);
-    return fmaxf(max3(b[0], b[1], b[2]), b[3]);
+    const float b0 = max3(a[0], a[1], a[2]), b1 = max3(a[3], a[4], a[5]), b2 = max3(a[6], a[7], a[8]);
+    const float b3 = fmaxf(a[9], a[10]);
+    return fmaxf(max3(b0, b1, b2), b3);
 }
 
-// The slow path addresses shared memory explicitly (32-bit shared-window addresses): it sits behind a call,
-// where generic pointers would compile to generic loads.
+// Shared memory is addressed explicitly (32-bit shared-window addresses).
 __device__ __forceinline__ float lds_f32(uint32_t a) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
     return v;
 }
+__device__ __forceinline__ float lds_f32_volatile(uint32_t a) {
+    float v;
+    asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32_volatile(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long lds_u64_volatile(uint32_t a) {
+    unsigned long long v;
+    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+    return v;
+}
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts_s32(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-
-constexpr uint32_t TC_LIST_STRIDE = TC_QUERIES * 4;   // bytes between consecutive entries of one query's list
-
-// Replace the minimum of the list of one query; the caller guarantees s > current minimum.  Returns the
-// new minimum = new threshold.
-__device__ __forceinline__ float tc_list_insert(uint32_t ls, uint32_t li, int len, float s, int idx) {
-    float m = lds_f32(ls);
-    int am = 0;
-    float second = CUDART_INF_F;
-    for (int e = 1; e < len; ++e) {
-        const float v = lds_f32(ls + e * TC_LIST_STRIDE);
-        if (v < m) {
-            second = m;
-            m = v;
-            am = e;
-        } else if (v < second) {
-            second = v;
-        }
-    }
-    sts_f32(ls + am * TC_LIST_STRIDE, s);
-    sts_s32(li + am * TC_LIST_STRIDE, idx);
-    return fminf(s, second);
+__device__ __forceinline__ void sts_u32_volatile(uint32_t a, uint32_t v) {
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
-
-// Exact FP32 score from the FP32 words of the operand tiles: the FMA chain of the FFMA filter
-// (accumulator initialised with h, coordinates in order).  Element k of a row sits
-// (k >> 2) * TC_CHUNK_BYTES + (k & 3) * 4 bytes after the row's first 16-byte chunk.
+__device__ __forceinline__ void sts_u64_volatile(uint32_t a, unsigned long long v) {
+    asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t atoms_add_u32(uint32_t a, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+    return old;
+}
 __device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
     return v;
 }
+
+constexpr uint32_t TC_LIST_STRIDE = TC_QUERIES * 4;   // bytes between consecutive entries of one query's list
+constexpr int TC_LMAX = MCE_TC_LIST_MAX;              // longest list: KCAP neighbours + margin
+constexpr int TC_BOOT = 9;                            // bootstrap network: the 9 largest coarse scores of a unit's first tile
+constexpr uint32_t TC_QCAP = 512;                     // hit-queue slots (power of two)
+constexpr unsigned long long TC_QEMPTY = 0xFFFFFFFFFFFFFFFFull;
+
+// Replace the minimum of the list of one query; the caller guarantees s > current minimum.  Returns the new
+// minimum = new threshold.  All entries are loaded before the first comparison (one shared-memory latency).
+template <int LM>
+__device__ __forceinline__ float tc_list_insert(uint32_t ls, uint32_t li, int len, float s, int idx) {
+    float v[LM];
+#pragma unroll
+    for (int e = 0; e < LM; ++e) v[e] = e < len ? lds_f32(ls + e * TC_LIST_STRIDE) : CUDART_INF_F;
+    float m = v[0];
+#pragma unroll
+    for (int e = 1; e < LM; ++e) m = fminf(m, v[e]);
+    int am = 0;
+#pragma unroll
+    for (int e = LM - 1; e >= 0; --e) am = (v[e] == m) ? e : am;   // first entry holding the minimum
+    float second = CUDART_INF_F;
+#pragma unroll
+    for (int e = 0; e < LM; ++e) second = fminf(second, e == am ? CUDART_INF_F : v[e]);
+    sts_f32(ls + am * TC_LIST_STRIDE, s);
+    sts_s32(li + am * TC_LIST_STRIDE, idx);
+    return fminf(s, second);
+}
+
+// Exact FP32 score: the FMA chain of the FFMA filter (accumulator initialised with h = h_hi + h_lo, coordinates in
+// order) on the FP32 words of the two operand rows.  Element k of a row sits (k >> 2) chunks after the row's first
+// 16-byte chunk.  Both rows are loaded completely before the chain starts.
+template <int KSTEPS>
+__device__ __forceinline__ float tc_score_chain(const float (&a)[8 * KSTEPS], const float (&b)[8 * KSTEPS], int d) {
+    float h_hi = 0.f, h_lo = 0.f;
+#pragma unroll
+    for (int k = 1; k < 8 * KSTEPS; ++k) {
+        h_hi = (k == d) ? b[k] : h_hi;
+        h_lo = (k == d + 1) ? b[k] : h_lo;
+    }
+    float acc = h_hi + h_lo;          // == h exactly (h_lo = h - h_hi is exact)
+#pragma unroll
+    for (int k = 0; k < 8 * KSTEPS; ++k)
+        if (k < d) acc = fmaf(a[k], b[k], acc);
+    return acc;
+}
+// both rows in shared memory (validation builds: the operand tile is still in its ring slot)
+template <int KSTEPS>
 __device__ __forceinline__ float tc_exact_score(uint32_t arow, uint32_t bcol, int d) {
-    const float h = lds_f32(bcol + (d >> 2) * TC_CHUNK_BYTES + (d & 3) * 4) +
-                    lds_f32(bcol + ((d + 1) >> 2) * TC_CHUNK_BYTES + ((d + 1) & 3) * 4);
-    float acc = h;
-    for (int c0 = 0; c0 < d; c0 += 4) {   // one 16-byte chunk of both rows per step, coordinates in order
-        const float4 a = lds_f32x4(arow + (c0 >> 2) * TC_CHUNK_BYTES);
-        const float4 b = lds_f32x4(bcol + (c0 >> 2) * TC_CHUNK_BYTES);
-        acc = fmaf(a.x, b.x, acc);
-        if (c0 + 1 < d) acc = fmaf(a.y, b.y, acc);
-        if (c0 + 2 < d) acc = fmaf(a.z, b.z, acc);
-        if (c0 + 3 < d) acc = fmaf(a.w, b.w, acc);
+    float a[8 * KSTEPS], b[8 * KSTEPS];
+#pragma unroll
+    for (int c = 0; c < 2 * KSTEPS; ++c) {
+        const float4 av = lds_f32x4(arow + c * TC_CHUNK_BYTES);
+        const float4 bv = lds_f32x4(bcol + c * TC_CHUNK_BYTES);
+        a[4 * c] = av.x; a[4 * c + 1] = av.y; a[4 * c + 2] = av.z; a[4 * c + 3] = av.w;
+        b[4 * c] = bv.x; b[4 * c + 1] = bv.y; b[4 * c + 2] = bv.z; b[4 * c + 3] = bv.w;
+    }
+    return tc_score_chain<KSTEPS>(a, b, d);
+}
+// query row in shared memory, reference row from the image in global memory (L2): the selection warp works on
+// references whose tile has long left the ring.  Four 16-byte chunks of both rows at a time.
+template <int KSTEPS>
+__device__ __forceinline__ float tc_exact_score_g(uint32_t arow, const float* __restrict__ brow, int d) {
+    constexpr int NC = 2 * KSTEPS;
+    float acc = __ldg(brow + (d >> 2) * TC_CHUNK_FLOATS + (d & 3)) +
+                __ldg(brow + ((d + 1) >> 2) * TC_CHUNK_FLOATS + ((d + 1) & 3));   // h_hi + h_lo == h exactly
+#pragma unroll
+    for (int c0 = 0; c0 < NC; c0 += 4) {
+        float4 bv[4], av[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (c0 + c < NC) bv[c] = __ldg(reinterpret_cast<const float4*>(brow + (c0 + c) * TC_CHUNK_FLOATS));
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (c0 + c < NC) av[c] = lds_f32x4(arow + (c0 + c) * TC_CHUNK_BYTES);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (c0 + c < NC) {
+                const int k = 4 * (c0 + c);
+                if (k < d) acc = fmaf(av[c].x, bv[c].x, acc);
+                if (k + 1 < d) acc = fmaf(av[c].y, bv[c].y, acc);
+                if (k + 2 < d) acc = fmaf(av[c].z, bv[c].z, acc);
+                if (k + 3 < d) acc = fmaf(av[c].w, bv[c].w, acc);
+            }
+        }
     }
     return acc;
 }
 
-// Slow path for one column that passed the coarse test.
-__device__ __noinline__ float tc_consider(uint32_t arow, uint32_t bcol, int d, float th, uint32_t ls, uint32_t li, int len,
-                                          int ridx, int self) {
-    const float s = tc_exact_score(arow, bcol, d);
-    if (s > th && ridx != self) th = tc_list_insert(ls, li, len, s, ridx);
-    return th;
-}
-
-struct TcEpiState {
-    uint32_t arow;       // shared address of this query's row in the A tile
-    uint32_t ls, li;     // shared addresses of entry 0 of this query's list (scores, indices)
-    float th, tcut, e_q;
-    float worst;         // CHECK: max |coarse - exact| / e over the pairs of this thread
-    unsigned int checked;
-    uint32_t full_bar, full_parity;   // "TMA bytes landed" barrier of the tile being processed
-    bool acquired;                    // ... already observed by this thread
-    int d, len, self;
-    float* dump_row;     // CHECK: where this query's coarse scores of the unit's first tile go (or null)
+// hit queue: epilogue lanes push (query, reference), the selection warp pops.  A slot holds TC_QEMPTY or an item, so
+// the slot itself says when its content is valid; `head` is published by the consumer after it has emptied slots.
+struct TcQueue {
+    uint32_t ctrl;    // shared address of {tail, head, done, pad}
+    uint32_t items;   // shared address of TC_QCAP 64-bit slots
 };
-
-// The epilogue learns about a tile through the accumulator barrier only; before it reads the operand tile
-// itself it observes the tile's own TMA barrier (already complete, so this never spins).
-__device__ __forceinline__ void tc_acquire_tile(TcEpiState& st) {
-    if (!st.acquired) {
-        tc_wait(st.full_bar, st.full_parity);
-        st.acquired = true;
+// The store sits INSIDE the wait loop: a lane whose position is within capacity must write its item before it can be
+// held at a reconvergence point by warp-mates that are still waiting for room (the consumer cannot pass an unwritten
+// slot, and those mates wait for the consumer).
+__device__ __forceinline__ void tc_push(const TcQueue& q, uint32_t query, uint32_t ridx) {
+    const uint32_t pos = atoms_add_u32(q.ctrl, 1u);
+    const unsigned long long item = ((unsigned long long)query << 32) | (unsigned long long)ridx;
+    const uint32_t addr = q.items + (pos & (TC_QCAP - 1)) * 8u;
+    long long t0 = 0;
+    for (bool first = true;; first = false) {
+        if (pos - lds_u32_volatile(q.ctrl + 4) < TC_QCAP) {
+            sts_u64_volatile(addr, item);
+            break;
+        }
+        if (first) t0 = clock64();
+        __nanosleep(64);
+        if (*reinterpret_cast<volatile unsigned int*>(&g_tc_stuck[0]) != 0u) break;
+        if (clock64() - t0 > 1000000000LL) {
+            if (atomicCAS(&g_tc_stuck[0], 0u, 2u) == 0u) {
+                g_tc_stuck[1] = pos;
+                g_tc_stuck[2] = lds_u32_volatile(q.ctrl + 4);
+                g_tc_stuck[3] = blockIdx.x;
+            }
+            break;
+        }
     }
 }
 
-// one group of 32 columns [col0, col0 + 32) of the tile at `tile`
-template <bool CHECK>
-__device__ __forceinline__ void tc_process(const uint32_t (&v)[32], int col0, uint32_t tile, int ridx0, TcEpiState& st) {
+struct TcEpiState {
+    uint32_t th_addr;    // shared address of this query's current threshold (written by the selection warp)
+    float e_q;           // bound on |coarse - exact| for this query
+    bool valid;
+    // validation builds only
+    uint32_t arow;       // shared address of this query's row in the A tile
+    float worst;         // max |coarse - exact| / e over the pairs of this thread
+    unsigned int checked;
+    uint32_t full_bar, full_parity;   // "TMA bytes landed" barrier of the tile being processed
+    int d;
+    float* dump_row;     // where this query's coarse scores of the unit's first tile go (or null)
+};
+
+// One accumulator half-tile of a query: 64 coarse scores in registers (the TMEM buffer has already been released).
+// The maxima of the two 32-column groups (2 x 17 FMNMX) are compared with the query's cut; only then (rare) the
+// passing columns are collected in bit masks and pushed to the hit queue.
+template <int KSTEPS, bool CHECK>
+__device__ __forceinline__ void tc_process_tile(const uint32_t (&v)[TC_HALF_COLS], uint32_t tile, int col_base, int ridx0, float tcut,
+                                                uint32_t query, const TcQueue& q, TcEpiState& st) {
     if constexpr (CHECK) {
         if (st.dump_row) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) st.dump_row[col0 + i] = __uint_as_float(v[i]);
+            for (int i = 0; i < TC_HALF_COLS; ++i) st.dump_row[col_base + i] = __uint_as_float(v[i]);
         }
-        if (st.th < CUDART_INF_F) {   // valid query
-            tc_acquire_tile(st);
+        if (st.valid) {
+            tc_wait(st.full_bar, st.full_parity);   // observe the tile's own TMA barrier before reading the tile
 #pragma unroll 1
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < TC_HALF_COLS; ++i) {
                 float coarse = 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
+                for (int j = 0; j < TC_HALF_COLS; ++j)
                     if (j == i) coarse = __uint_as_float(v[j]);
-                const int col = col0 + i;
-                const float ex = tc_exact_score(st.arow, tile + (col >> 3) * TC_ROWGROUP_BYTES + (col & 7) * 16, st.d);
+                const int col = col_base + i;
+                const float ex = tc_exact_score<KSTEPS>(st.arow, tile + (col >> 3) * TC_ROWGROUP_BYTES + (col & 7) * 16, st.d);
                 if (ex > -CUDART_INF_F && st.e_q > 0.f) {
                     st.worst = fmaxf(st.worst, fabsf(coarse - ex) / st.e_q);
                     st.checked++;
@@ -172,41 +264,56 @@ __device__ __forceinline__ void tc_process(const uint32_t (&v)[32], int col0, ui
             }
         }
     }
-    float b[4];
-    const float m = max32(v, b);
-    if (m > st.tcut) {
-        tc_acquire_tile(st);
-        // only the sub-blocks whose maximum passed are scanned (th only rises, so a stale maximum is conservative)
+    float m[2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (b[j] > st.tcut) {
+    for (int g = 0; g < 2; ++g) m[g] = max32(&v[32 * g]);
+    if (fmaxf(m[0], m[1]) > tcut) {
+        uint32_t mask[2];
 #pragma unroll
-                for (int ii = 0; ii < 9; ++ii) {
-                    const int i = 9 * j + ii;
-                    if (i < 32 && __uint_as_float(v[i < 32 ? i : 31]) > st.tcut) {
-                        const int col = col0 + i;
-                        st.th = tc_consider(st.arow, tile + (col >> 3) * TC_ROWGROUP_BYTES + (col & 7) * 16, st.d, st.th,
-                                            st.ls, st.li, st.len, ridx0 + col, st.self);
-                        st.tcut = st.th - st.e_q;
-                    }
-                }
+        for (int g = 0; g < 2; ++g) {
+            mask[g] = 0u;
+            if (m[g] > tcut) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mask[g] |= (__uint_as_float(v[32 * g + i]) > tcut) ? (1u << i) : 0u;
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            uint32_t mk = mask[g];
+            while (mk) {
+                const int col = col_base + 32 * g + (__ffs((int)mk) - 1);
+                mk &= mk - 1u;
+                tc_push(q, query, (uint32_t)(ridx0 + col));
             }
         }
     }
 }
 
+// Descending insertion network: keeps the TC_BOOT largest values seen.
+__device__ __forceinline__ void tc_boot_insert(float (&t)[TC_BOOT], float x) {
+#pragma unroll
+    for (int i = 0; i < TC_BOOT; ++i) {
+        const float hi = fmaxf(t[i], x);
+        x = fminf(t[i], x);
+        t[i] = hi;
+    }
+}
+
 // TL builds record clock64() of the hand-over points of the first 1024 tiles of CTA 0 into tp.timeline ([tile][16]):
-// MMA warp 0 tile landed, 1/3 accumulator free (query block 0/1), 2/4 MMAs + commit issued; epilogue warp 0 (block 0)
+// MMA warps 0 tile landed, 1 accumulator free, 2 MMAs + commit issued; epilogue warp 0 (query block 0, columns 0-63)
 // 5 accumulator full, 6 accumulator released, 7 tile done; epilogue warp 4 (block 1) 8, 9, 10; producer 11 slot free
+// MODE: 0 production, 1 validation (every pair also evaluated exactly, first tile dumped), 2 timeline, 3 / 4 timing
+// experiments whose results are garbage (3: the epilogue skips the TMEM loads, 4: loads without the threshold test)
 #define TC_MARK(IT, SLOT)                                                                            \
     do {                                                                                             \
-        if constexpr (TL) {                                                                          \
+        if constexpr (MODE == 2) {                                                                          \
             if (blockIdx.x == 0 && (IT) < 1024 && lane == 0) tp.timeline[(IT) * 16 + (SLOT)] = clock64(); \
         }                                                                                            \
     } while (0)
 
-template <int KSTEPS, bool CHECK, bool TL>
+template <int KSTEPS, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFilterParams tp) {
+    constexpr bool CHECK = MODE == 1;
     constexpr int K = KSTEPS * 8;
     constexpr uint32_t TILE_BYTES = (uint32_t)K * TC_TILE_REFS * 4;   // K/4 chunks of 2 KB
     constexpr uint32_t A_MB_BYTES = (uint32_t)K * TC_QBLK * 4;
@@ -221,11 +328,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * A_MB_BYTES + (size_t)NS * TILE_BYTES);
     uint64_t* bar_full = bars;              // [NS]  TMA bytes of a tile have landed
     uint64_t* bar_free = bars + NS;         // [NS]  all epilogue warps are done with the tile in the slot
-    uint64_t* bar_acc_full = bars + 2 * NS; // [2 buffers][2 query blocks]  the MMAs of a tile for a query block have completed
-    uint64_t* bar_acc_free = bars + 2 * NS + 4;   // [2 buffers][2 query blocks]  its four epilogue warps have read the accumulator
+    uint64_t* bar_acc_full = bars + 2 * NS; // [2 buffers]  the MMAs of a tile (both query blocks) have completed
+    uint64_t* bar_acc_free = bars + 2 * NS + 4;   // [2 buffers]  the eight epilogue warps have read the accumulator
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 8);
-    float* ls = reinterpret_cast<float*>(tmem_slot + 4);
-    int* li = reinterpret_cast<int*>(ls + (size_t)L * TC_QUERIES);
+    uint32_t* qctrl = tmem_slot + 4;        // hit queue: tail, head, done, pad
+    unsigned long long* qitems = reinterpret_cast<unsigned long long*>(qctrl + 4);
+    float* th_s = reinterpret_cast<float*>(qitems + TC_QCAP);   // [256] current threshold of every query
+    float* ls = th_s + TC_QUERIES;                              // [L][256] list scores
+    int* li = reinterpret_cast<int*>(ls + (size_t)L * TC_QUERIES);   // [L][256] list indices
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -257,20 +367,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
             mbar_init(smem_u32(&bar_free[s]), TC_EPI_WARPS);
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(smem_u32(&bar_acc_full[2 * b]), 1);
-            mbar_init(smem_u32(&bar_acc_full[2 * b + 1]), 1);
-            mbar_init(smem_u32(&bar_acc_free[2 * b]), TC_EPI_WARPS / 2);
-            mbar_init(smem_u32(&bar_acc_free[2 * b + 1]), TC_EPI_WARPS / 2);
+            mbar_init(smem_u32(&bar_acc_full[b]), 1);
+            mbar_init(smem_u32(&bar_acc_free[b]), TC_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        qctrl[0] = 0u; qctrl[1] = 0u; qctrl[2] = 0u; qctrl[3] = 0u;
     }
+    for (uint32_t i = tid; i < TC_QCAP; i += TC_THREADS) qitems[i] = TC_QEMPTY;
+    TcQueue queue{smem_u32(qctrl), smem_u32(qitems)};
     TcEpiState st;
     st.worst = 0.f;
     st.checked = 0;
     st.dump_row = nullptr;
-    const long long ql = (long long)qblock * TC_QUERIES + tid;   // epilogue threads: local query id
+    const int qslot = tid & (TC_QUERIES - 1), half = (tid >> 8) & 1;   // epilogue threads: query of the block, column half
+    const long long ql = (long long)qblock * TC_QUERIES + qslot;         // local query id
     if (warp < TC_EPI_WARPS) {
-        const int mb = tid >> 7, row = tid & 127;
+        const int mb = qslot >> 7, row = qslot & 127;
         const bool valid = ql < nq;
         const double* src = p.yq + (p.q_begin + (valid ? ql : 0)) * p.d;
         float* arow = a_sm + mb * (K * TC_QBLK) + (row >> 3) * 32 + (row & 7) * 4;
@@ -292,22 +404,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
                 }
                 w[i] = x;
             }
-            *reinterpret_cast<float4*>(arow + c * TC_CHUNK_FLOATS) = make_float4(w[0], w[1], w[2], w[3]);
+            if (half == 0) *reinterpret_cast<float4*>(arow + c * TC_CHUNK_FLOATS) = make_float4(w[0], w[1], w[2], w[3]);
         }
         const float rmax = __uint_as_float(*tp.rmax_bits);
         const float qn = sqrtf(qn2) * 1.000001f;
         st.arow = smem_u32(arow);
-        st.ls = smem_u32(ls + tid);
-        st.li = smem_u32(li + tid);
+        st.th_addr = smem_u32(th_s + qslot);
         st.e_q = tp.slack_qr * qn * rmax + tp.slack_rr * rmax * rmax;
-        st.th = valid ? -CUDART_INF_F : CUDART_INF_F;
-        st.tcut = st.th;
+        st.valid = valid;
         st.d = p.d;
-        st.len = L;
-        st.self = p.self_exclude ? (int)(p.q_begin + ql + p.self_offset) : -0x7fffffff;
-        for (int e = 0; e < L; ++e) {
-            ls[e * TC_QUERIES + tid] = -CUDART_INF_F;
-            li[e * TC_QUERIES + tid] = -1;
+        if (half == 0) {
+            th_s[qslot] = -CUDART_INF_F;
+            for (int e = 0; e < L; ++e) {
+                ls[e * TC_QUERIES + qslot] = -CUDART_INF_F;
+                li[e * TC_QUERIES + qslot] = -1;
+            }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // A tile: generic-proxy stores -> tensor-core reads
     }
@@ -324,9 +435,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
             for (int n = 0; n < nt; ++n) {
                 if (round > 0) {
                     const uint32_t fb = smem_u32(&bar_free[slot]);
-                    tc_wait(fb, (uint32_t)(round - 1) & 1u);
+                    tc_wait_relaxed(fb, (uint32_t)(round - 1) & 1u);
                 }
-                if constexpr (TL) {
+                if constexpr (MODE == 2) {
                     if (blockIdx.x == 0 && n < 1024) tp.timeline[n * 16 + 11] = clock64();
                 }
                 const uint32_t bar = smem_u32(&bar_full[slot]);
@@ -338,136 +449,235 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
                 }
             }
         }
-    } else if (warp == TC_MMA_WARP) {
-        const uint32_t a_base = smem_u32(a_sm), ring_base = smem_u32(ring);
-        // debug bits of swap_offsets: 1 = exchange the two byte offsets, 2 = descriptor version field 0 instead of 1
-        const uint32_t lbo = (tp.swap_offsets & 1) ? TC_ROWGROUP_BYTES : TC_CHUNK_BYTES;
-        const uint32_t sbo = (tp.swap_offsets & 1) ? TC_CHUNK_BYTES : TC_ROWGROUP_BYTES;
-        const uint32_t dver = (tp.swap_offsets & 2) ? 0u : 1u;
-        int slot = 0, round = 0;
-        for (int it = 0; it < nt; ++it) {
-            const int buf = it & 1;
-            {
-                const uint32_t fb = smem_u32(&bar_full[slot]);
-                tc_wait(fb, (uint32_t)round & 1u);
-            }
-            TC_MARK(it, 0);
-#pragma unroll
-            for (int mb = 0; mb < 2; ++mb) {
-                if (it >= 2) {   // the query block's epilogue warps have drained this buffer (tile it - 2)
-                    const uint32_t ab = smem_u32(&bar_acc_free[2 * buf + mb]);
-                    tc_wait(ab, (uint32_t)((it >> 1) - 1) & 1u);
-                }
-                TC_MARK(it, 1 + 2 * mb);
+    } else if (warp == TC_MMA_WARP || warp == TC_MMA_WARP2) {
+        // One hand-over per tile: wait for the tile and for the accumulator buffer, issue the 2 x KSTEPS MMAs of both
+        // query blocks, one commit.  The waits and the issue cost ~400 cycles of one thread per tile, more than the
+        // MMAs themselves, so with tp.mma_warps == 2 a second warp issues the odd tiles (buffer 1) independently.
+        const int nw = tp.mma_warps == 2 ? 2 : 1;
+        const int first = warp == TC_MMA_WARP ? 0 : 1;
+        if (warp == TC_MMA_WARP || nw == 2) {
+            const uint32_t a_base = smem_u32(a_sm), ring_base = smem_u32(ring);
+            // debug bits of swap_offsets: 1 = exchange the two byte offsets, 2 = descriptor version field 0 instead of 1
+            const uint32_t lbo = (tp.swap_offsets & 1) ? TC_ROWGROUP_BYTES : TC_CHUNK_BYTES;
+            const uint32_t sbo = (tp.swap_offsets & 1) ? TC_CHUNK_BYTES : TC_ROWGROUP_BYTES;
+            const uint32_t dver = (tp.swap_offsets & 2) ? 0u : 1u;
+            const uint64_t desc_hi = tc_smem_desc(0, lbo, sbo, dver);
+            for (int it = first; it < nt; it += nw) {
+                const int buf = it & 1;
+                const int slot = it % NS, round = it / NS;
+                tc_wait(smem_u32(&bar_full[slot]), (uint32_t)round & 1u);
+                TC_MARK(it, 0);
+                if (it >= 2)   // the epilogue warps have drained this buffer (tile it - 2)
+                    tc_wait(smem_u32(&bar_acc_free[buf]), (uint32_t)((it >> 1) - 1) & 1u);
+                TC_MARK(it, 1);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u + (uint32_t)mb * 128u;
+                    const uint32_t b_addr = ring_base + (uint32_t)slot * TILE_BYTES;
 #pragma unroll
-                    for (int ks = 0; ks < KSTEPS; ++ks) {
-                        const uint64_t adesc = tc_smem_desc(a_base + mb * A_MB_BYTES + ks * KSTEP_BYTES, lbo, sbo, dver);
-                        const uint64_t bdesc = tc_smem_desc(ring_base + (uint32_t)slot * TILE_BYTES + ks * KSTEP_BYTES, lbo, sbo, dver);
-                        umma_tf32(d_tmem, adesc, bdesc, TC_IDESC, ks > 0 ? 1u : 0u);
+                    for (int mb = 0; mb < 2; ++mb) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u + (uint32_t)mb * 128u;
+#pragma unroll
+                        for (int ks = 0; ks < KSTEPS; ++ks) {
+                            const uint64_t adesc = desc_hi | (uint64_t)(((a_base + mb * A_MB_BYTES + ks * KSTEP_BYTES) >> 4) & 0x3FFFu);
+                            const uint64_t bdesc = desc_hi | (uint64_t)(((b_addr + ks * KSTEP_BYTES) >> 4) & 0x3FFFu);
+                            umma_tf32(d_tmem, adesc, bdesc, TC_IDESC, ks > 0 ? 1u : 0u);
+                        }
                     }
-                    umma_commit(smem_u32(&bar_acc_full[2 * buf + mb]));   // this query block's warps can start
+                    umma_commit(smem_u32(&bar_acc_full[buf]));
                 }
                 __syncwarp();
-                TC_MARK(it, 2 + 2 * mb);
+                TC_MARK(it, 2);
             }
+        }
+    } else if (warp == TC_SELECT_WARP) {
+        // Selection warp: pops up to 32 hits at a time, evaluates them exactly (one lane each: query row from the A
+        // tile, reference row from the image in L2) and maintains the lists and thresholds of all 256 queries.
+        const uint32_t ctrl = queue.ctrl;
+        const float* img = p.tiles;
+        const int d = p.d;
+        uint32_t head = 0;
+        for (;;) {
+            const uint32_t done = lds_u32_volatile(ctrl + 8);
+            const uint32_t tail = lds_u32_volatile(ctrl);
+            const uint32_t avail = tail - head;
+            if (avail == 0) {
+                if (done == (uint32_t)TC_EPI_WARPS) break;
+                if (*reinterpret_cast<volatile unsigned int*>(&g_tc_stuck[0]) != 0u) break;
+                __nanosleep(128);
+                continue;
+            }
+            // pop the written prefix of the next 32 positions: a reserved slot may not have been written yet, and its
+            // owner may be held up by warp-mates that wait for `head` to move, so never wait for a slot here
+            const uint32_t nres = avail < 32u ? avail : 32u;
+            unsigned long long item = TC_QEMPTY;
+            const uint32_t addr = queue.items + ((head + lane) & (TC_QCAP - 1)) * 8u;
+            if ((uint32_t)lane < nres) item = lds_u64_volatile(addr);
+            const uint32_t unwritten = __ballot_sync(0xffffffffu, item == TC_QEMPTY);
+            const uint32_t n = unwritten ? (uint32_t)(__ffs((int)unwritten) - 1) : 32u;
+            if (n == 0u) {
+                if (*reinterpret_cast<volatile unsigned int*>(&g_tc_stuck[0]) != 0u) break;
+                __nanosleep(32);
+                continue;
+            }
+            const bool has = (uint32_t)lane < n;
+            if (has) sts_u64_volatile(addr, TC_QEMPTY);
+            head += n;
+            __threadfence_block();
             __syncwarp();
-            if (++slot == NS) {
-                slot = 0;
-                ++round;
+            if (lane == 0) sts_u32_volatile(ctrl + 4, head);
+            const uint32_t q = has ? (uint32_t)(item >> 32) : 0u;
+            const int ridx = has ? (int)(uint32_t)item : 0;
+            float s = -CUDART_INF_F;
+            if (has) {
+                const uint32_t arow = smem_u32(a_sm) + (q >> 7) * A_MB_BYTES + ((q & 127u) >> 3) * TC_ROWGROUP_BYTES + (q & 7u) * 16u;
+                const float* brow = img + (size_t)(ridx >> 7) * (K * TC_TILE_REFS) + ((ridx & 127) >> 3) * 32 + (ridx & 7) * 4;
+                s = tc_exact_score_g<KSTEPS>(arow, brow, d);
+                const int self = p.self_exclude ? (int)(p.q_begin + (long long)qblock * TC_QUERIES + q + p.self_offset) : -0x7fffffff;
+                if (ridx == self) s = -CUDART_INF_F;
+            }
+            // hits of the same query are inserted one after the other (rank within the batch)
+            const uint32_t peers = __match_any_sync(0xffffffffu, has ? q : (0x80000000u | (uint32_t)lane));
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            const int maxrank = __reduce_max_sync(0xffffffffu, rank);
+            for (int r = 0; r <= maxrank; ++r) {
+                if (has && rank == r) {
+                    const uint32_t tha = smem_u32(th_s) + q * 4u;
+                    const float th = lds_f32(tha);
+                    if (s > th) {
+                        const uint32_t lsa = smem_u32(ls) + q * 4u, lia = smem_u32(li) + q * 4u;
+                        const float nmin = L <= 8 ? tc_list_insert<8>(lsa, lia, L, s, ridx) : tc_list_insert<TC_LMAX>(lsa, lia, L, s, ridx);
+                        sts_f32(tha, fmaxf(th, nmin));   // the bootstrap floor stays in force while the list fills
+                    }
+                }
+                __syncwarp();
             }
         }
     } else {
-        const int mb = warp >> 2, quad = warp & 3;
-        const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)mb * 128u;
-        int slot = 0, round = 0;
-        for (int it = 0; it < nt; ++it) {
-            const int buf = it & 1;
-            {
-                const uint32_t fb = smem_u32(&bar_acc_full[2 * buf + mb]);
-                tc_wait(fb, (uint32_t)(it >> 1) & 1u);
-            }
-            __syncwarp();   // lanes may leave the spin loop at different times
+        const int mb = (warp >> 2) & 1, quad = warp & 3;
+        const int col_base = half * TC_HALF_COLS;
+        const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mb * 128 + col_base);
+        const uint32_t acc_full0 = smem_u32(&bar_acc_full[0]), acc_free0 = smem_u32(&bar_acc_free[0]);
+        const uint32_t slot_bar0 = smem_u32(&bar_free[0]), slot_bar_end = slot_bar0 + (uint32_t)NS * 8u;
+        const uint32_t ring0 = smem_u32(ring);
+        // invalid queries never pass: th - e_q is NaN (th starts at -inf) or +inf
+        const float e_q = st.valid ? st.e_q : -CUDART_INF_F;
+
+        if (MODE <= 2 && nt > 0 && L + 1 <= TC_BOOT) {
+            // Bootstrap: the (L+1)-th largest coarse score c among this thread's columns of the unit's first tile.
+            // At least L references other than the query itself have an exact score >= c - e, so the threshold can
+            // start from there instead of -inf (the larger of the two halves wins): the first tile then yields a
+            // handful of hits per query instead of 128.  The tile is processed again by the loop below.
+            tc_wait(acc_full0, 0u);
+            __syncwarp();
             tc_fence_after();
-            if (quad == 0) TC_MARK(it, 5 + 3 * mb);
-            st.full_bar = smem_u32(&bar_full[slot]);
-            st.full_parity = (uint32_t)round & 1u;
-            st.acquired = false;
-            if constexpr (CHECK) st.dump_row = (tp.dump && blockIdx.x == 0 && it == 0) ? tp.dump + (size_t)tid * TC_TILE_REFS : nullptr;
-            const uint32_t taddr = tlane + (uint32_t)buf * 256u;
-            const uint32_t tile = smem_u32(ring) + (uint32_t)slot * TILE_BYTES;
-            const int ridx0 = (t0 + it) * TC_TILE_REFS;
-            if (tp.perf_mode == 0) {
-                // tcgen05.ld is warp-collective: the warp is re-converged after every (divergent) slow path
-                uint32_t va[32], vb[32];
-                tmem_ld32(taddr, va);
-                tmem_wait_ld(va);
-                tmem_ld32(taddr + 32, vb);
-                tc_process<CHECK>(va, 0, tile, ridx0, st);
-                __syncwarp();
-                tmem_wait_ld(vb);
-                tmem_ld32(taddr + 64, va);
-                tc_process<CHECK>(vb, 32, tile, ridx0, st);
-                __syncwarp();
-                tmem_wait_ld(va);
-                tmem_ld32(taddr + 96, vb);
-                tc_process<CHECK>(va, 64, tile, ridx0, st);
-                __syncwarp();
-                tmem_wait_ld(vb);
-                // the accumulator buffer has been read by this warp: hand it back to the MMA issuer
+            float t[TC_BOOT];
+#pragma unroll
+            for (int i = 0; i < TC_BOOT; ++i) t[i] = -CUDART_INF_F;
+#pragma unroll 1
+            for (int c = 0; c < TC_HALF_COLS / 32; ++c) {
+                uint32_t w[32];
+                tmem_ld32(tlane + 32 * c, w);
+                tmem_wait_ld(w);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) tc_boot_insert(t, __uint_as_float(w[i]));
+            }
+            float c0 = -CUDART_INF_F;
+#pragma unroll
+            for (int i = 0; i < TC_BOOT; ++i) c0 = (i == L) ? t[i] : c0;
+            if (st.valid && c0 > -CUDART_INF_F) {
+                const float th0 = c0 - st.e_q * 1.001f - 1e-30f;
+                // float maximum through compare-and-swap on the bit pattern (twice per query and unit)
+                uint32_t old = lds_u32_volatile(st.th_addr);
+                while (th0 > __uint_as_float(old)) {
+                    uint32_t seen;
+                    asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(seen) : "r"(st.th_addr), "r"(old), "r"(__float_as_uint(th0)) : "memory");
+                    if (seen == old) break;
+                    old = seen;
+                }
+            }
+            __threadfence_block();
+        }
+
+        // Tile loop, unrolled over the two accumulator buffers so that every address is loop-invariant.  Per tile and
+        // thread: one barrier wait, one TMEM load of this thread's 64 columns, two arrivals (accumulator buffer back
+        // to the MMA issuer, ring slot back to the producer), 35 FMNMX and one compare.
+        uint32_t parity = 0u, slot_bar = slot_bar0;
+        int ridx0 = t0 * TC_TILE_REFS;
+        auto one_tile = [&](const int buf, const int it) {
+            tc_wait(acc_full0 + 8u * buf, parity);
+            __syncwarp();   // lanes may leave the wait at different times; the TMEM load is warp-collective
+            tc_fence_after();
+            if (quad == 0 && half == 0) TC_MARK(it, 5 + 3 * mb);
+            const uint32_t taddr = tlane + 256u * buf;
+            if constexpr (MODE <= 2) {
+                const float tcut = lds_f32_volatile(st.th_addr) - e_q;
+                uint32_t v[TC_HALF_COLS];
+                tmem_ld64_wait(taddr, v);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bar_acc_free[2 * buf + mb]));
-                if (quad == 0) TC_MARK(it, 6 + 3 * mb);
-                tc_process<CHECK>(vb, 96, tile, ridx0, st);
+                if (lane == 0) {
+                    mbar_arrive(acc_free0 + 8u * buf);
+                    if (!CHECK) mbar_arrive(slot_bar);
+                }
+                if (quad == 0 && half == 0) TC_MARK(it, 6 + 3 * mb);
+                if constexpr (CHECK) {
+                    const int slot = (int)((slot_bar - slot_bar0) >> 3);
+                    st.full_bar = smem_u32(&bar_full[slot]);
+                    st.full_parity = (uint32_t)(it / NS) & 1u;
+                    st.dump_row = (tp.dump && blockIdx.x == 0 && it == 0) ? tp.dump + (size_t)qslot * TC_TILE_REFS : nullptr;
+                    tc_process_tile<KSTEPS, CHECK>(v, ring0 + (uint32_t)slot * TILE_BYTES, col_base, ridx0, tcut, (uint32_t)qslot, queue, st);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(slot_bar);
+                } else {
+                    tc_process_tile<KSTEPS, CHECK>(v, 0u, col_base, ridx0, tcut, (uint32_t)qslot, queue, st);
+                }
             } else {
-                if (tp.perf_mode == 2) {   // the four loads alone
-                    uint32_t va[32], vb[32];
-                    tmem_ld32(taddr, va);
-                    tmem_ld32(taddr + 32, vb);
-                    tmem_wait_ld(va);
-                    tmem_wait_ld(vb);
-                    st.checked ^= va[0] ^ vb[31];
-                    tmem_ld32(taddr + 64, va);
-                    tmem_ld32(taddr + 96, vb);
-                    tmem_wait_ld(va);
-                    tmem_wait_ld(vb);
-                    st.checked ^= va[5] ^ vb[17];
+                if constexpr (MODE == 4) {   // the loads alone
+                    uint32_t v[TC_HALF_COLS];
+                    tmem_ld64_wait(taddr, v);
+                    st.checked ^= v[0] ^ v[63];
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bar_acc_free[2 * buf + mb]));
-                if (quad == 0) TC_MARK(it, 6 + 3 * mb);
+                if (lane == 0) {
+                    mbar_arrive(acc_free0 + 8u * buf);
+                    mbar_arrive(slot_bar);
+                }
+                if (quad == 0 && half == 0) TC_MARK(it, 6 + 3 * mb);
             }
-            // the slow path reads the operand tile: release the ring slot only now
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bar_free[slot]));
-            if (quad == 0) TC_MARK(it, 7 + 3 * mb);
-            if (++slot == NS) {
-                slot = 0;
-                ++round;
-            }
+            if (quad == 0 && half == 0) TC_MARK(it, 7 + 3 * mb);
+            slot_bar += 8u;
+            if (slot_bar == slot_bar_end) slot_bar = slot_bar0;
+            ridx0 += TC_TILE_REFS;
+        };
+#pragma unroll 1
+        for (int it = 0; it < nt; it += 2) {
+            one_tile(0, it);
+            if (it + 1 < nt) one_tile(1, it + 1);
+            parity ^= 1u;
         }
-        if (ql < nq) {
-            p.cand_th[cand_th_offset(rchunk, ql, p.nq_pad, p.ntail_pad, p.tail_q0)] = st.th;
-            for (int e = 0; e < L; ++e)
-                p.cand_idx[cand_idx_offset(rchunk, e, ql, L, p.nq_pad, p.ntail_pad, p.tail_q0)] = li[e * TC_QUERIES + tid];
-        }
+        // every hit of this warp is in the queue: tell the selection warp
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) atoms_add_u32(queue.ctrl + 8, 1u);
         if constexpr (CHECK) {
             if (tp.debug) {
                 atomicMax(&tp.debug[0], __float_as_uint(st.worst));   // non-negative floats order like their bits
                 atomicAdd(&tp.debug[1], st.checked);
             }
-        } else if (tp.perf_mode == 2 && st.checked == 0x9e3779b9u && tp.debug) {
+        } else if (MODE == 4 && st.checked == 0x9e3779b9u && tp.debug) {
             tp.debug[1] = st.checked;   // keeps the loads of the timing experiment alive
         }
     }
 
-    // ---- tear-down -------------------------------------------------------------------------------
+    // ---- lists out, tear-down ----------------------------------------------------------------------
     tc_fence_before();
-    __syncthreads();
+    __syncthreads();   // the selection warp has drained the queue: lists and thresholds are final
+    if (warp < TC_EPI_WARPS && half == 0 && ql < nq) {
+        p.cand_th[cand_th_offset(rchunk, ql, p.nq_pad, p.ntail_pad, p.tail_q0)] = th_s[qslot];
+        for (int e = 0; e < L; ++e)
+            p.cand_idx[cand_idx_offset(rchunk, e, ql, L, p.nq_pad, p.ntail_pad, p.tail_q0)] = li[e * TC_QUERIES + qslot];
+    }
     if (warp == TC_MMA_WARP) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TC_TMEM_COLS);
@@ -475,30 +685,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
 }
 
 size_t tc_fixed_smem(int K, int list_len) {
-    return (size_t)2 * K * TC_QBLK * 4 + (size_t)(2 * 8 + 8) * sizeof(uint64_t) + 16 +
-           (size_t)list_len * TC_QUERIES * (sizeof(float) + sizeof(int));
+    return (size_t)2 * K * TC_QBLK * 4 + (size_t)(2 * 8 + 8) * sizeof(uint64_t) + 16 + 16 + (size_t)TC_QCAP * 8 +
+           (size_t)TC_QUERIES * 4 + (size_t)list_len * TC_QUERIES * (sizeof(float) + sizeof(int));
+}
+
+template <int KSTEPS, int MODE>
+int tc_launch_mode(const TcFilterParams& tp, unsigned grid, size_t smem, cudaStream_t st) {
+    auto kern = knn_filter_tc_kernel<KSTEPS, MODE>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    kern<<<grid, TC_THREADS, smem, st>>>(tp);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 template <int KSTEPS>
 int tc_launch_k(const TcFilterParams& tp, unsigned grid, size_t smem, cudaStream_t st) {
-    if constexpr (KSTEPS == 2) {
-        if (tp.timeline) {   // timing diagnostics (ndim 7..14 only)
-            auto kern = knn_filter_tc_kernel<KSTEPS, false, true>;
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-            kern<<<grid, TC_THREADS, smem, st>>>(tp);
-            return cudaGetLastError() == cudaSuccess ? 0 : -1;
-        }
+    if constexpr (KSTEPS == 2) {   // diagnostics exist for ndim 7..14 only
+        if (tp.timeline) return tc_launch_mode<KSTEPS, 2>(tp, grid, smem, st);
+        if (tp.perf_mode == 1) return tc_launch_mode<KSTEPS, 3>(tp, grid, smem, st);
+        if (tp.perf_mode == 2) return tc_launch_mode<KSTEPS, 4>(tp, grid, smem, st);
     }
-    if (tp.check) {
-        auto kern = knn_filter_tc_kernel<KSTEPS, true, false>;
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        kern<<<grid, TC_THREADS, smem, st>>>(tp);
-    } else {
-        auto kern = knn_filter_tc_kernel<KSTEPS, false, false>;
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        kern<<<grid, TC_THREADS, smem, st>>>(tp);
-    }
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    if (tp.check) return tc_launch_mode<KSTEPS, 1>(tp, grid, smem, st);
+    return tc_launch_mode<KSTEPS, 0>(tp, grid, smem, st);
 }
 
 // reference image: one thread per reference row
@@ -540,6 +747,17 @@ __global__ void __launch_bounds__(128) tc_image_kernel(const double* __restrict_
 
 }  // namespace
 
+// Give-up record of the barrier waits (tcgen05.cuh): copies {flag, a, b, block} to `out` and clears it on the device.
+int tc_read_stuck(unsigned int (&out)[4], cudaStream_t st) {
+    if (cudaMemcpyFromSymbolAsync(out, g_tc_stuck, sizeof(out), 0, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    if (out[0] != 0u) {
+        const unsigned int zero[4] = {0u, 0u, 0u, 0u};
+        if (cudaMemcpyToSymbol(g_tc_stuck, zero, sizeof(zero)) != cudaSuccess) return -1;
+    }
+    return 0;
+}
+
 size_t tc_image_bytes(long long n_ref, int d) {
     const long long ntiles = (n_ref + TC_TILE_REFS - 1) / TC_TILE_REFS;
     return (size_t)ntiles * tc_kpad(d) * TC_TILE_REFS * sizeof(float);
@@ -554,7 +772,7 @@ void launch_tc_image(const double* y64, const float* ffma_tiles, long long n_ref
 }
 
 int tc_filter_query(int d, int list_len, int want_stages, int* queries_per_cta, int* smem_bytes, int* ctas_per_sm, int* stages) {
-    if (d < 1 || d > MAX_DIM) return -1;
+    if (d < 1 || d > MAX_DIM || list_len > TC_LMAX) return -1;
     const int K = tc_kpad(d);
     const size_t tile = (size_t)K * TC_TILE_REFS * 4;
     const size_t fixed = tc_fixed_smem(K, list_len);

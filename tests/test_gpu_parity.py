@@ -315,40 +315,81 @@ def test_golden_knn_arrays(ctx):
     assert np.abs(out['logE'] - g.mle).max() < LOGE_TIGHT
 
 
-def test_full_size_properties_cfg2(ctx):
-    """BASELINE cfg2 (N=1e6, d=10, kmax=4, auto) at full size through size-independent properties."""
-    n, d, kmax = 1000000, 10, 4
-    chain, info = gaussian_chain(n, d, seed=0)
+def _full_size_properties(ctx, n, d, kmax, cross, seed, nspot=48, nshard=3000, analytic_tol=None):
+    """A BASELINE configuration at full size through size-independent properties: sortedness and index ranges, spot
+    rows against an exhaustive FP64 numpy scan in the library's own whitened coordinates, a shard of rows against the
+    library's exhaustive FP64 search (bit for bit), permutation invariance, and shard combination."""
+    chain, info = gaussian_chain(n * (2 if cross else 1), d, seed=seed)
     s, l, w = np.ascontiguousarray(chain[:, 2:]), -chain[:, 1], chain[:, 0]
-    out = ctx.evidence(s, l, w, kmax, log_sum_w=math.log(w.sum()), want_knn=True)
+    s1, l1, w1 = s[:n], l[:n], w[:n]
+    s2 = s[n:] if cross else None
+    lsw = math.log(w1.sum())
+    out = ctx.evidence(s1, l1, w1, kmax, ref=s2, log_sum_w=lsw, want_knn=True)
     dk, ix = out['dknn'], out['idx']
-    assert np.all(np.diff(dk, axis=1) >= 0) and np.all(dk[:, 0] == 0) and np.all(dk[:, 1] > 0)
-    assert np.array_equal(ix[:, 0], np.arange(n)) and ix.min() >= 0 and ix.max() < n
-    assert not np.any(ix[:, 1:] == np.arange(n)[:, None])
-    # analytic evidence of the synthetic posterior (estimator bias bound, SURVEY section 8d M2)
-    assert np.abs(out['logE'] - info['lnZ']).max() < 0.1
+    n_ref = len(s2) if cross else n
+    assert dk.shape == (n, kmax + 1)
+    assert np.all(np.diff(dk, axis=1) >= 0) and ix.min() >= 0 and ix.max() < n_ref
+    c0 = 0 if cross else 1           # first column holding a true neighbour
+    if not cross:
+        assert np.all(dk[:, 0] == 0) and np.all(dk[:, 1] > 0)
+        assert np.array_equal(ix[:, 0], np.arange(n))
+        assert not np.any(ix[:, 1:] == np.arange(n)[:, None])
+    if analytic_tol is not None and not cross:
+        assert np.abs(out['logE'] - info['lnZ']).max() < analytic_tol
     # spot rows against an exhaustive FP64 numpy scan in the library's own whitened coordinates
     cs = O.covariance_stats(s)
     L = np.linalg.cholesky(cs['cov'])
-    y = np.linalg.solve(L, (s - s.mean(0)).T).T
-    rows = np.random.default_rng(1).choice(n, 48, replace=False)
+    mu = s.mean(0)
+    y1 = np.linalg.solve(L, (s1 - mu).T).T
+    y2 = np.linalg.solve(L, (s2 - mu).T).T if cross else y1
+    rows = np.random.default_rng(1).choice(n, nspot, replace=False)
+    ncol = kmax + 1 - c0
     for r in rows:
-        d2 = ((y - y[r]) ** 2).sum(1)
-        d2[r] = np.inf
-        nn = np.argsort(d2, kind='stable')[:kmax]
-        assert np.array_equal(ix[r, 1:], nn)
-        np.testing.assert_allclose(dk[r, 1:], np.sqrt(d2[nn]), rtol=1e-11)
-    # mutual consistency: the distance stored for (i -> j) is the distance recomputed from the rows
-    j = ix[rows, 1]
-    np.testing.assert_allclose(dk[rows, 1], np.sqrt(((y[rows] - y[j]) ** 2).sum(1)), rtol=1e-11)
+        d2 = ((y2 - y1[r]) ** 2).sum(1)
+        if not cross:
+            d2[r] = np.inf
+        nn = np.argsort(d2, kind='stable')[:ncol]
+        assert np.array_equal(ix[r, c0:], nn)
+        np.testing.assert_allclose(dk[r, c0:], np.sqrt(d2[nn]), rtol=1e-11)
+    # a shard of rows through the library's exhaustive FP64 search: identical to the last bit
+    lo = n // 3
+    ex = ctx.evidence(s1, l1, w1, kmax, ref=s2, log_sum_w=lsw, want_knn=True, q_range=(lo, lo + nshard), exact_only=True)
+    np.testing.assert_array_equal(ex['idx'], ix[lo:lo + nshard])
+    np.testing.assert_array_equal(ex['dknn'], dk[lo:lo + nshard])
     # permutation invariance of the estimator (different tiles, chunks and summation order)
     perm = np.random.default_rng(2).permutation(n)
-    out2 = ctx.evidence(s[perm], l[perm], w[perm], kmax, log_sum_w=math.log(w.sum()))
+    ref_p = s2[np.random.default_rng(3).permutation(n_ref)] if cross else None
+    out2 = ctx.evidence(s1[perm], l1[perm], w1[perm], kmax, ref=ref_p, log_sum_w=lsw)
     assert np.abs(out2['logE'] - out['logE']).max() < 1e-9
     # two half-shards combine to the same answer
-    parts = [ctx.evidence(s, l, w, kmax, q_range=r, want_partials=True)['partials']
+    parts = [ctx.evidence(s1, l1, w1, kmax, ref=s2, q_range=r, want_partials=True)['partials']
              for r in ((0, n // 2), (n // 2, n))]
-    loge, _ = _lib.finalize(_lib.combine_partials(np.array(parts)), d, False, n, math.log(w.sum()),
-                            out['log_jacobian'], 0.0)
+    loge, _ = _lib.finalize(_lib.combine_partials(np.array(parts)), d, cross, n, lsw, out['log_jacobian'], 0.0)
     assert np.abs(loge - out['logE']).max() < 1e-11
     assert out['stats']['rows_rescanned'] < 1000
+    return out
+
+
+@pytest.mark.parametrize('engine', [0, 2])
+def test_full_size_properties_cfg2(ctx, engine):
+    """BASELINE cfg2 (N=1e6, d=10, kmax=4, auto) at full size, with the FFMA filter and with the automatic choice
+    (the tcgen05 filter at this size)."""
+    ctx.set_option('filter_engine', engine)
+    try:
+        out = _full_size_properties(ctx, 1000000, 10, 4, False, seed=0, analytic_tol=0.1)
+        assert (out['stats']['filter_mode'] == 16) == (engine == 2)
+    finally:
+        ctx.set_option('filter_engine', 2)
+
+
+def test_full_size_properties_cfg3(ctx):
+    """BASELINE cfg3 shape (cross evidence, d=27, 1e6 x 1e6, kmax=4) at full size."""
+    out = _full_size_properties(ctx, 1000000, 27, 4, True, seed=3)
+    assert out['stats']['filter_mode'] == 16
+
+
+def test_full_size_properties_cfg5_shape(ctx):
+    """BASELINE cfg5 shape (auto, d=20, kmax=8: nine columns, candidate lists of ten) at N=2e6, the per-GPU reference-set
+    size class of the 8-GPU scaling run."""
+    out = _full_size_properties(ctx, 2000000, 20, 8, False, seed=5, nspot=32, nshard=2000)
+    assert out['stats']['filter_mode'] == 16

@@ -1,10 +1,8 @@
-"""Parity of the opt-in tcgen05 engine of the neighbour filter (``filter_engine`` = 1) with the FP64 oracle
-and with the default FFMA engine.
-
-The engine has not run on hardware yet (it was written after this round's GPU budget was spent), so these
-tests only run when MCE_TEST_TC=1; the bring-up order is tools/tc_bringup.py first (small case under a
-timeout), then this file.  Bar: bit-exact neighbours, as for the FFMA engine, and a coarse-score error that
-stays inside the allowance used by the filter (``tc_check_ratio`` < 1).
+"""Parity of the tcgen05 engine of the neighbour filter (``filter_engine`` = 1) with the FP64 oracle and with the
+FFMA engine.  The library picks the engine per problem (``filter_engine`` = 2, the default); these tests force the
+tensor-core engine on every shape, including the small ones the automatic rule leaves to the FFMA filter.
+Bar: bit-exact neighbours, as for the FFMA engine, and a coarse-score error that stays inside the allowance used by
+the filter (``tc_check_ratio`` < 1).
 """
 import os
 
@@ -14,9 +12,7 @@ import pytest
 from oracle import mce_oracle as O
 from mcevidence_b200.synthetic import gaussian_chain
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('MCE_TEST_TC') != '1',
-                                 reason='tcgen05 filter engine is opt-in until validated on hardware (MCE_TEST_TC=1)')]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture
@@ -25,7 +21,7 @@ def tc(ctx):
     try:
         yield ctx
     finally:
-        for name, v in (('filter_engine', 0), ('tc_check', 0), ('tc_slack_percent', 100), ('ref_chunks', -1)):
+        for name, v in (('filter_engine', 2), ('tc_check', 0), ('tc_slack_percent', 100), ('ref_chunks', -1)):
             ctx.set_option(name, v)
 
 

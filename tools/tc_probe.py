@@ -21,6 +21,7 @@ ap.add_argument('--qn', type=int, default=37888)
 ap.add_argument('--k', type=int, default=5)
 ap.add_argument('--stages', type=int, nargs='*', default=[2, 3, 4, 6, 8])
 ap.add_argument('--modes', type=int, nargs='*', default=[1, 2, 0])
+ap.add_argument('--mma-warps', type=int, nargs='*', default=[1, 2])
 ap.add_argument('--out', default=None)
 a = ap.parse_args()
 chain, _ = gaussian_chain(a.n, a.d, seed=0)
@@ -28,12 +29,14 @@ x = np.ascontiguousarray(chain[:, 2:])
 ctx = _lib.Context(0)
 ctx.set_option('filter_engine', 1)
 rows = []
-for stages in a.stages:
-    ctx.set_option('tc_stages', stages)
-    for mode in a.modes:
-        ctx.set_option('tc_perf_mode', mode)
-        ms = min(ctx.knn(x, a.k, q_range=(0, a.qn) if a.qn else None)[2]['ms_filter'] for _ in range(3))
-        rows.append({'n': a.n, 'd': a.d, 'qn': a.qn, 'stages': stages, 'perf_mode': mode, 'ms_filter': ms})
-        print(rows[-1], flush=True)
+for mw in a.mma_warps:
+    ctx.set_option('tc_mma_warps', mw)
+    for stages in a.stages:
+        ctx.set_option('tc_stages', stages)
+        for mode in a.modes:
+            ctx.set_option('tc_perf_mode', mode)
+            ms = min(ctx.knn(x, a.k, q_range=(0, a.qn) if a.qn else None)[2]['ms_filter'] for _ in range(3))
+            rows.append({'n': a.n, 'd': a.d, 'qn': a.qn, 'mma_warps': mw, 'stages': stages, 'perf_mode': mode, 'ms_filter': ms})
+            print(rows[-1], flush=True)
 if a.out:
     json.dump(rows, open(a.out, 'w'), indent=1)

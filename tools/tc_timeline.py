@@ -18,12 +18,15 @@ ap.add_argument('--n', type=int, default=1000000)
 ap.add_argument('--d', type=int, default=10)
 ap.add_argument('--qn', type=int, default=37888)
 ap.add_argument('--out', default='gpurun_out/tc_timeline.npz')
+ap.add_argument('--mma-warps', type=int, default=2)
+ap.add_argument('--skip', type=int, default=0, help='leading tiles of CTA 0 left out of the statistics')
 a = ap.parse_args()
 chain, _ = gaussian_chain(a.n, a.d, seed=0)
 x = np.ascontiguousarray(chain[:, 2:])
 ctx = _lib.Context(0)
 ctx.set_option('filter_engine', 1)
 ctx.set_option('tc_timeline', 1)
+ctx.set_option('tc_mma_warps', a.mma_warps)
 res = {}
 for mode in (0, 1):
     ctx.set_option('tc_perf_mode', mode)
@@ -35,7 +38,7 @@ for mode in (0, 1):
     tt = t[100:900].astype(np.float64)
     per_tile = (tt[-1, 0] - tt[0, 0]) / (len(tt) - 1)
     print('mode %d: filter %.3f ms, %.0f clk per tile' % (mode, st['ms_filter'], per_tile))
-    names = ['mma:landed', 'mma:free0', 'mma:issued0', 'mma:free1', 'mma:issued1', 'epi0:full', 'epi0:released', 'epi0:done',
+    names = ['mma:landed', 'mma:free', 'mma:issued', 'unused', 'unused', 'epi0:full', 'epi0:released', 'epi0:done',
              'epi1:full', 'epi1:released', 'epi1:done', 'prod:slotfree']
     base = tt[:, 0:1]
     rel = tt[:, :12] - base
@@ -43,9 +46,9 @@ for mode in (0, 1):
         print('  %-14s mean %+8.0f  p10 %+8.0f  p90 %+8.0f   (relative to mma:landed of the same tile)' % (
             nm, rel[:, i].mean(), np.percentile(rel[:, i], 10), np.percentile(rel[:, i], 90)))
     # latencies of the chain
-    print('  issue0 -> epi0:full (MMA + commit + wake)      mean %.0f' % (tt[:, 5] - tt[:, 2]).mean())
-    print('  issue1 -> epi1:full                            mean %.0f' % (tt[:, 8] - tt[:, 4]).mean())
-    print('  epi0:released(it) -> mma:free0(it+2) observed  mean %.0f' % (tt[2:, 1] - tt[:-2, 6]).mean())
+    print('  issued -> epi0:full (MMA + commit + wake)      mean %.0f' % (tt[:, 5] - tt[:, 2]).mean())
+    print('  issued -> epi1:full                            mean %.0f' % (tt[:, 8] - tt[:, 2]).mean())
+    print('  epi0:released(it) -> mma:free(it+2) observed   mean %.0f' % (tt[2:, 1] - tt[:-2, 6]).mean())
     print('  epi0:full -> released (hold)                   mean %.0f' % (tt[:, 6] - tt[:, 5]).mean())
     print('  epi0:full -> done                              mean %.0f' % (tt[:, 7] - tt[:, 5]).mean())
 np.savez(a.out, **res)
