@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MCE_ABI_VERSION 1
+#define MCE_ABI_VERSION 2
 
 #define MCE_OK              0
 #define MCE_ERR_ARG        -1   /* bad argument (message says which) */
@@ -80,6 +80,18 @@ typedef struct mce_problem {
     double log_jacobian;     /* log J, read only when W != NULL */
     double log_sum_w;        /* log sum of adjusted_weights of s1 (MCEvidence.py:1126) */
     double log_prior_volume; /* MCEvidence.py:1017-1020 */
+    /* Burn-in / thinning / split applied on the device (MCEvidence.py:174-249, 350-391, 417-445): when query_rows is
+       not NULL, `query` points to a BASE array of n_query_base rows (the concatenated chain) and sample i of s1 is its
+       row query_rows[i], i < n_query -- the rows kept by burn-in, thinning and the random split, in the order the
+       reference's fancy indexing would produce.  The base array is uploaded once and the rows are gathered by the
+       covariance and whitening kernels as they load; no gathered copy is made on either side.  ref_rows likewise for
+       `ref`; when ref == query (same base pointer and stride: the two halves of one split chain) the base is
+       uploaded once.  logl and weights stay per-sample host vectors of n_query entries (thinning replaces the weights,
+       :427-445).  NULL, NULL, 0, 0: the arrays are the sample sets themselves.  Host-array problems only. */
+    const int64_t *query_rows;
+    const int64_t *ref_rows;
+    int64_t n_query_base;
+    int64_t n_ref_base;
 } mce_problem;
 
 typedef struct mce_stats {
@@ -127,7 +139,8 @@ void mce_ctx_destroy(mce_ctx *ctx);
    stream; pass cudaStreamLegacy ((void*)1) for the default stream.  NULL restores the context's own stream. */
 int  mce_ctx_set_stream(mce_ctx *ctx, void *cuda_stream);
 /* Tuning knobs: "filter_tq", "filter_tr", "filter_packed", "filter_sync" (kernel mode 0/1/2), "ref_chunks"
-   (uniform split of the reference set), "list_margin". -1 = automatic.
+   (uniform split of the reference set), "list_margin". -1 = automatic.  "batch_lanes" (1..32, default 8): concurrent
+   problems of mce_evidence_batch.
    "filter_engine": 2 = chosen per problem (default: the tcgen05 filter for ndim >= 4 and at least ~6e8 pairs, 2e8
    from ndim 10 on -- where it was measured faster on B200 -- otherwise the FP32 FFMA filter), 0 = FFMA filter,
    1 = tcgen05 tensor-core filter (TF32 coarse scores in TMEM, exact FP32 evaluation of the columns that pass; same
@@ -149,7 +162,19 @@ int  mce_ctx_get_debug(mce_ctx *ctx, const char *name, double *value);
 int  mce_ctx_get_debug_array(mce_ctx *ctx, const char *name, float *out, int64_t capacity, int64_t *n);
 
 int  mce_evidence(mce_ctx *ctx, const mce_problem *problem, mce_result *result);
+/* n independent problems (planck_mcevidence.py:306-359).  Host-array problems overlap on up to "batch_lanes" (option,
+   default 8) internal streams with their own workspaces: inputs are uploaded and kernels enqueued for every problem
+   without waiting for results, one synchronisation at the end; results are bit-identical to n mce_evidence calls.
+   stats of a batched problem carry only ms_total and the configuration fields. */
 int  mce_evidence_batch(mce_ctx *ctx, int n, const mce_problem *problems, mce_result *results);
+/* Batch-size sweep (set_batch / the batch loop of MCEvidence.py:808-840, 1039-1045): results[b] = the evidence of the
+   first batch_rows[b] rows of `query` (auto mode: neighbours among those rows; cross mode: in all of ref), with the
+   whitening of the whole problem (W == NULL: covariance of ALL n_query rows U ref, as covtype='all' does), SumW =
+   log_sum_w for every batch and S = batch_rows[b] in the normalisation.  One upload, one whitening and one pass of the
+   filter over the largest batch serve every size: the reference set is cut at the tile-aligned batch sizes, batch b
+   merges the candidates of the ranges inside its prefix in the FP64 re-rank.  Each result equals the mce_evidence call
+   on the prefix with the same explicit W / mu, bit for bit.  q_begin/q_end must be 0; dknn/idx are not returned. */
+int  mce_evidence_sweep(mce_ctx *ctx, const mce_problem *problem, int nbatch, const int64_t *batch_rows, mce_result *results);
 
 /* k nearest neighbours with sklearn's contract: dknn/idx are (q_end-q_begin, n_neighbors), ascending.
    Auto mode (ref == NULL): column 0 is the row itself at distance 0, as when the reference queries the

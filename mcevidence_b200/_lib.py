@@ -36,6 +36,7 @@ class Problem(C.Structure):
         ('d', C.c_int32), ('kmax', C.c_int32), ('flags', C.c_int32), ('reserved', C.c_int32),
         ('W', C.c_void_p), ('W_ref', C.c_void_p), ('mu', C.c_void_p),
         ('log_jacobian', C.c_double), ('log_sum_w', C.c_double), ('log_prior_volume', C.c_double),
+        ('query_rows', C.c_void_p), ('ref_rows', C.c_void_p), ('n_query_base', C.c_int64), ('n_ref_base', C.c_int64),
     ]
 
 
@@ -94,6 +95,7 @@ def load_library():
         lib.mce_ctx_get_debug_array.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
         lib.mce_evidence.argtypes = [C.c_void_p, C.POINTER(Problem), C.POINTER(Result)]
         lib.mce_evidence_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(Problem), C.POINTER(Result)]
+        lib.mce_evidence_sweep.argtypes = [C.c_void_p, C.POINTER(Problem), C.c_int, c_int64_p, C.POINTER(Result)]
         lib.mce_knn.argtypes = [C.c_void_p, C.POINTER(Problem), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Stats)]
         lib.mce_combine_partials.argtypes = [C.c_int, C.c_int, c_double_p, c_double_p]
         lib.mce_finalize.argtypes = [c_double_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_double,
@@ -134,6 +136,8 @@ def _f64(a, name, allow_f32=False):
 
 class Context:
     """One CUDA stream + workspace on one device (``mce_ctx``)."""
+
+    supports_row_maps = True     # query_rows / ref_rows: burn-in, thinning and split applied by the device (N2)
 
     def __init__(self, device=0):
         self._lib = load_library()
@@ -184,7 +188,9 @@ class Context:
         return out.reshape(-1, 128) if n.value else out
 
     def _problem(self, query, ref, logl, weights, ndim, kmax, W, W_ref, mu, log_jacobian, log_sum_w,
-                 log_prior_volume, q_range, flags, keep):
+                 log_prior_volume, q_range, flags, keep, query_rows=None, ref_rows=None):
+        """``query_rows`` / ``ref_rows``: ``query`` / ``ref`` are BASE arrays and the sample sets are their rows
+        ``query_rows`` / ``ref_rows`` (burn-in, thinning and split applied by the device as it loads)."""
         p = Problem()
         # float32 sample arrays are passed as they are (MCE_FLAG_F32_SAMPLES) when query and ref agree
         f32 = np.asarray(query).dtype == np.float32 and (ref is None or np.asarray(ref).dtype == np.float32)
@@ -200,6 +206,10 @@ class Context:
             raise ValueError('ndim=%d exceeds the %d sample columns' % (ndim, query.shape[1]))
         p.query = _ptr(query)
         p.n_query, p.ld_query = query.shape[0], query.strides[0] // isz
+        if query_rows is not None:
+            query_rows = np.ascontiguousarray(query_rows, dtype=np.int64).reshape(-1)
+            keep.append(query_rows)
+            p.query_rows, p.n_query_base, p.n_query = _ptr(query_rows), query.shape[0], query_rows.shape[0]
         if ref is not None:
             ref = _f64(ref, 'ref', allow_f32=f32)
             keep.append(ref)
@@ -207,11 +217,15 @@ class Context:
                 raise ValueError('ref must be 2-D with at least ndim columns')
             p.ref = _ptr(ref)
             p.n_ref, p.ld_ref = ref.shape[0], ref.strides[0] // isz
+            if ref_rows is not None:
+                ref_rows = np.ascontiguousarray(ref_rows, dtype=np.int64).reshape(-1)
+                keep.append(ref_rows)
+                p.ref_rows, p.n_ref_base, p.n_ref = _ptr(ref_rows), ref.shape[0], ref_rows.shape[0]
         for name, arr in (('logl', logl), ('weights', weights)):
             if arr is not None:
                 arr = _f64(arr, name).reshape(-1)
-                if arr.shape[0] != query.shape[0]:
-                    raise ValueError('%s has %d entries for %d samples' % (name, arr.shape[0], query.shape[0]))
+                if arr.shape[0] != p.n_query:
+                    raise ValueError('%s has %d entries for %d samples' % (name, arr.shape[0], p.n_query))
                 keep.append(arr)
                 setattr(p, name, _ptr(arr))
         for name, arr, shape in (('W', W, (ndim, ndim)), ('W_ref', W_ref, (ndim, ndim)), ('mu', mu, (ndim,))):
@@ -230,13 +244,13 @@ class Context:
 
     def evidence(self, query, logl, weights, kmax, ref=None, ndim=None, W=None, W_ref=None, mu=None,
                  log_jacobian=0.0, log_sum_w=0.0, log_prior_volume=0.0, q_range=None, want_knn=False,
-                 want_partials=False, exact_only=False):
+                 want_partials=False, exact_only=False, query_rows=None, ref_rows=None):
         """``mce_evidence`` on host arrays.  Returns a dict with ``logE`` (kmax-1), ``var_logE``,
         ``log_jacobian``, ``stats`` and optionally ``dknn``/``idx``/``partials``."""
         keep = []
         flags = (FLAG_PARTIALS if want_partials else 0) | (FLAG_EXACT_ONLY if exact_only else 0)
         p, nq = self._problem(query, ref, logl, weights, ndim, kmax, W, W_ref, mu, log_jacobian, log_sum_w,
-                              log_prior_volume, q_range, flags, keep)
+                              log_prior_volume, q_range, flags, keep, query_rows, ref_rows)
         kk = max(2, int(kmax))
         r = Result()
         loge = np.empty(kk - 1)
@@ -278,8 +292,35 @@ class Context:
             o['stats'] = rarr[i].stats.as_dict()
         return outs
 
+    def evidence_sweep(self, query, logl, weights, kmax, batch_rows, ref=None, ndim=None, W=None, W_ref=None, mu=None,
+                       log_jacobian=0.0, log_sum_w=0.0, log_prior_volume=0.0, want_partials=False, query_rows=None,
+                       ref_rows=None):
+        """``mce_evidence_sweep``: the evidence of the first ``batch_rows[b]`` rows of ``query`` for every b (the batch
+        loop of ``MCEvidence.py:1039-1045``) from one upload, one whitening and one pass of the filter.  Returns a list
+        of result dicts (``logE``, ``var_logE``, ``log_jacobian``, ``stats``), one per batch size."""
+        keep = []
+        rows = np.ascontiguousarray(batch_rows, dtype=np.int64).reshape(-1)
+        nb = int(rows.shape[0])
+        p, _ = self._problem(query, ref, logl, weights, ndim, kmax, W, W_ref, mu, log_jacobian, log_sum_w,
+                             log_prior_volume, None, FLAG_PARTIALS if want_partials else 0, keep, query_rows, ref_rows)
+        kk = max(2, int(kmax))
+        rarr = (Result * nb)()
+        outs = []
+        for b in range(nb):
+            o = {'logE': np.empty(kk - 1), 'var_logE': np.empty(kk - 1)}
+            rarr[b].logE, rarr[b].var_logE = _ptr(o['logE']), _ptr(o['var_logE'])
+            if want_partials:
+                o['partials'] = np.empty((kk - 1, 3))
+                rarr[b].partials = _ptr(o['partials'])
+            outs.append(o)
+        _check(self._lib, self._lib.mce_evidence_sweep(self._h, C.byref(p), nb, rows.ctypes.data_as(c_int64_p), rarr))
+        for b, o in enumerate(outs):
+            o['log_jacobian'] = rarr[b].log_jacobian
+            o['stats'] = rarr[b].stats.as_dict()
+        return outs
+
     def knn(self, query, n_neighbors, ref=None, ndim=None, W=None, W_ref=None, mu=None, q_range=None,
-            exact_only=False, identity=False):
+            exact_only=False, identity=False, query_rows=None, ref_rows=None):
         """``mce_knn``: ``(dknn, idx, stats)`` with sklearn's ``kneighbors`` contract.
         ``identity=True`` searches the coordinates as given (W = I, mu = 0)."""
         keep = []
@@ -288,7 +329,7 @@ class Context:
         if identity:
             W = np.eye(nd)
         p, nq = self._problem(query, ref, None, None, nd, 2, W, W_ref, mu, 0.0, 0.0, 0.0, q_range,
-                              FLAG_EXACT_ONLY if exact_only else 0, keep)
+                              FLAG_EXACT_ONLY if exact_only else 0, keep, query_rows, ref_rows)
         dknn = np.empty((nq, int(n_neighbors)))
         idx = np.empty((nq, int(n_neighbors)), dtype=np.int64)
         st = Stats()

@@ -33,13 +33,50 @@ FORMAT = "%(levelname)s:%(filename)s.%(funcName)s():%(lineno)-8s %(message)s"
 
 
 class data_set(object):
-    """One partition of the samples (``MCEvidence.py:99-104``)."""
+    """One partition of the samples (``MCEvidence.py:99-104``).
+
+    The partition is either an array (``samples``) or -- next-row N2, burn-in / thinning / split applied on the
+    device -- a *row map* into the concatenated chain: ``base`` (the parameter columns of the chain, a view) and
+    ``rows`` (the rows burn-in, thinning and the random split kept, in the reference's order).  ``samples``
+    materialises ``base[rows]`` on first use, so every caller of the reference's attribute keeps working; the hot
+    path asks :meth:`device_view` instead and lets the covariance / whitening kernels gather the rows as they load,
+    so no gathered host copy of the chain is ever made.
+    """
 
     def __init__(self, d):
-        self.samples = d['samples']
+        self._samples = d.get('samples')
+        self._base = d.get('base')
+        self._rows = d.get('rows')
         self.weights = d['weights']
         self.loglikes = d['loglikes']
         self.adjusted_weights = d['aweights']
+
+    @property
+    def samples(self):
+        if self._samples is None and self._base is not None:
+            self._samples = self._base if self._rows is None else self._base[self._rows]
+        return self._samples
+
+    @samples.setter
+    def samples(self, value):
+        self._samples, self._base, self._rows = value, None, None
+
+    @property
+    def nrows(self):
+        if self._base is not None:
+            return self._base.shape[0] if self._rows is None else len(self._rows)
+        return 0 if self._samples is None else self._samples.shape[0]
+
+    @property
+    def ncols(self):
+        a = self._base if self._base is not None else self._samples
+        return 0 if a is None else a.shape[1]
+
+    def device_view(self):
+        """``(base, rows)`` when the partition is still a row map of the chain (``rows`` None: all rows), else None."""
+        if self._base is None or self._rows is None:
+            return None
+        return self._base, self._rows
 
 
 def read_chain_file(fname, nthreads=0):
@@ -140,32 +177,45 @@ class SamplesMIXIN(object):
         if burnlen > 0:
             self.chains = [self.removeBurn(burnlen, chain=c) for c in self.chains]
         self.chain_offsets = np.cumsum(np.array([0] + [c.shape[0] for c in self.chains]))
-        self.samples = np.concatenate(self.chains)
-        if np.abs(thinlen) > 0:
-            thinned = self.thin(nthin=thinlen, chain=self.samples)
-            if thinned is not None:      # thin() returns None for nthin == 1 (MCEvidence.py:296-297)
-                self.samples = thinned
+        self.samples = np.concatenate(self.chains)          # the one host pass over the chain (burn-in = views)
+        rows, weights = None, None
+        if np.abs(thinlen) > 0 and thinlen != 1:             # thin() is a no-op for nthin == 1 (MCEvidence.py:296-297)
+            # thinning keeps a row map and the new weights; the rows themselves are gathered on the device
+            weights, rows = self.get_thin_index(thinlen, self.samples[:, self.iw])
+            self.logger.info('Thinning with thin length={} #old_chain={},#new_chain={}'.format(
+                thinlen, len(self.samples), len(weights)))
+            rows = np.asarray(rows, dtype=np.int64)
+            weights = np.asarray(weights, dtype=np.float64)
         self.chains = None
-        return self.chain_split(self.samples)
+        return self.chain_split(self.samples, rows=rows, weights=weights)
 
-    def chain_split(self, s):
-        """Random s1/s2 split from the global numpy RNG (``MCEvidence.py:221-249``)."""
+    def chain_split(self, s, rows=None, weights=None):
+        """Random s1/s2 split from the global numpy RNG (``MCEvidence.py:221-249``).
+
+        ``rows`` / ``weights``: the rows of ``s`` kept by thinning and their new weights (None: every row with its
+        own weight column).  The partitions are row maps into ``s`` (see :class:`data_set`)."""
+        nrow = len(s) if rows is None else len(rows)
+        w_all = s[:, self.iw] if weights is None else weights
+        base = s[:, self.itheta:]
+
+        def part(sel):
+            r = sel if rows is None else rows[sel]
+            return {'weights': w_all[sel], 'loglikes': s[r, self.ilike], 'base': base, 'rows': r, 'ichain': sel}
+
         if self.split:
-            nrow = len(s)
             ix = np.random.choice(nrow, size=int(nrow * self.s1frac), replace=False)
             mask = np.ones(nrow, dtype=bool)
             mask[ix] = False
             not_ix = np.flatnonzero(mask)            # == np.setxor1d(range(nrow), ix)
             self.logger.info('{} chain with nrow={} split to ns1={}, ns2={}'.format(
                 self.nchains, nrow, len(ix), len(not_ix)))
-            s1, s2 = s[ix, :], s[not_ix, :]
-            s1_dict = {'weights': s1[:, self.iw], 'loglikes': s1[:, self.ilike],
-                       'samples': s1[:, self.itheta:], 'ichain': ix}
-            s2_dict = {'weights': s2[:, self.iw], 'loglikes': s2[:, self.ilike],
-                       'samples': s2[:, self.itheta:], 'ichain': not_ix}
+            s1_dict, s2_dict = part(ix), part(not_ix)
         else:
-            s1_dict = {'weights': s[:, self.iw], 'loglikes': s[:, self.ilike],
-                       'samples': s[:, self.itheta:], 'ichain': range(len(s))}
+            if rows is None:
+                s1_dict = {'weights': s[:, self.iw], 'loglikes': s[:, self.ilike], 'samples': base,
+                           'ichain': range(len(s))}
+            else:
+                s1_dict = part(np.arange(nrow))
             s2_dict = {'weights': None, 'loglikes': None, 'samples': None, 'ichain': None}
         s1_dict['aweights'] = np.copy(s1_dict['weights'])
         s2_dict['aweights'] = np.copy(s2_dict['weights']) if s2_dict['weights'] is not None else None
@@ -173,12 +223,12 @@ class SamplesMIXIN(object):
 
     # -- accessors ----------------------------------------------------------
     def get_shape(self, name='s1'):
-        def shape_of(s):
-            return s.shape if s is not None else (0, 0)
+        def shape_of(ds):
+            return (ds.nrows, ds.ncols)
         if name in ('s1', 's2'):
-            return shape_of(self.data[name].samples)
-        s1 = shape_of(self.data['s1'].samples)
-        s2 = shape_of(self.data['s2'].samples)
+            return shape_of(self.data[name])
+        s1 = shape_of(self.data['s1'])
+        s2 = shape_of(self.data['s2'])
         return (s1[0] + s2[0], s1[1])
 
     def arrays(self, name='s1'):

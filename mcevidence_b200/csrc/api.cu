@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -69,15 +70,43 @@ struct DevBuf {
 };
 
 struct DevScalars {
+    // head: what the host reads back after a call (one copy of DEV_HEAD_BYTES)
     double out[3 * (MCE_MAX_NEIGHBOURS + 1)];
     double logj;
-    double mean[MCE_MAX_DIM];
-    double W[MCE_MAX_DIM * MCE_MAX_DIM];
-    double W_ref[MCE_MAX_DIM * MCE_MAX_DIM];
     int status;
     int nflagged;
     unsigned int rmax_bits;
     int pad;
+    // device-only tail
+    double mean[MCE_MAX_DIM];
+    double W[MCE_MAX_DIM * MCE_MAX_DIM];
+    double W_ref[MCE_MAX_DIM * MCE_MAX_DIM];
+};
+constexpr size_t DEV_HEAD_BYTES = offsetof(DevScalars, mean);
+
+// pinned host buffer, grow-only
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return MCE_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        if (cudaMallocHost(&p, bytes + 256) != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            return fail(MCE_ERR_NOMEM, "cudaMallocHost of %zu bytes failed", bytes);
+        }
+        cap = bytes + 256;
+        return MCE_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
 enum { EV_START, EV_H2D, EV_COV, EV_WHITEN, EV_FILTER, EV_RERANK, EV_EXACT, EV_REDUCE, EV_END, EV_COUNT };
@@ -98,8 +127,17 @@ struct mce_ctx {
     std::vector<float> dbg_tc_dump;   // tc_check: coarse scores of unit 0, tile 0 ([256 queries][128 references])
     DevBuf xq, xr, logl, w, yr, yq, tiles, tc_tiles, tc_debug, tc_dump, cand_idx, cand_th, dknn, idx, flagged, covpart, redpart, scal,
         sink, exact;
-    DevScalars* hscal = nullptr;  // pinned
+    DevBuf rows_q, rows_r;          // row maps of the query / reference set (burn-in, thinning, split on the device)
+    DevBuf sweep_meta, sweep_out;   // batch-size sweep: boundaries / per-batch (max, sum, sum2) triples
+    DevScalars* hscal = nullptr;    // pinned
+    PinBuf hres;                    // pinned result heads of a batch (one per problem) / sweep triples
+    PinBuf hmeta;                   // pinned staging of the sweep metadata
     cudaEvent_t ev[EV_COUNT] = {};
+    // mce_evidence_batch: independent problems run concurrently on `lanes` child contexts (own stream + workspace each)
+    std::vector<mce_ctx*> lanes;
+    std::vector<cudaEvent_t> ev_pool;   // start / end events of the problems of a batch
+    int opt_lanes = 8;
+    int share = 1;                  // the work-split model assumes sm_count / share SMs (several problems in flight)
 };
 
 namespace {
@@ -123,8 +161,20 @@ int validate(const mce_problem* p, bool need_evidence) {
         if (!p->logl || !p->weights) return fail(MCE_ERR_ARG, "problem.logl / problem.weights is NULL");
     }
     if (p->W_ref && !p->W) return fail(MCE_ERR_ARG, "W_ref given without W");
+    if (p->query_rows || p->ref_rows) {
+        if (p->flags & MCE_FLAG_DEVICE_PTRS) return fail(MCE_ERR_ARG, "row maps (query_rows / ref_rows) need host arrays");
+        if (p->query_rows && p->n_query_base < 1) return fail(MCE_ERR_ARG, "query_rows given with n_query_base=%lld", (long long)p->n_query_base);
+        if (p->ref_rows && (!p->ref || p->n_ref_base < 1))
+            return fail(MCE_ERR_ARG, "ref_rows given without ref or with n_ref_base=%lld", (long long)p->n_ref_base);
+    }
     return MCE_OK;
 }
+
+struct Sweep {               // batch-size sweep: one pass serves every batch size (MCEvidence.py:1039-1045)
+    int nb = 0;
+    const int64_t* rows = nullptr;   // S_b: batch b uses the first S_b rows of the query set
+    mce_result* results = nullptr;   // nb results
+};
 
 struct Run {
     // inputs
@@ -135,6 +185,23 @@ struct Run {
     int64_t* idx_out;
     mce_result* res;
     mce_stats* stats;
+    const Sweep* sweep = nullptr;
+    DevScalars* hres = nullptr;      // pinned destination of the result head (default: the context's own)
+    bool batch_lane = false;         // part of mce_evidence_batch: only the total time is measured
+};
+
+// State of an enqueued problem that is needed again after the stream has been synchronised.
+struct Pending {
+    Run r;
+    bool use_tc = false, exact_only = false, cross = false;
+    int d = 0, nk = 0, launches = 0;
+    long long nq_all = 0, nq = 0, n_ref = 0;
+    FilterConfig cfg{0, 0, 0, 0};
+    int chunks = 1, list_len = 0, nfull = 0, nqblocks = 0, smem = 0, ctas = 0;
+    DevScalars* hres = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // start / end events of a batch lane problem (else the context's own)
+    std::vector<long long> sweep_rows;   // S_b per batch (sweep only)
+    double* h_sweep_out = nullptr;       // pinned [nb][nk][3]
 };
 
 // Work decomposition model (calibrated on B200, profiles/r01_filter_variants.md).  Query blocks [0, nfull)
@@ -174,20 +241,42 @@ SplitPlan plan_split(long long nqblocks, int sm_count, int qpc, int ctas, long l
     return best;
 }
 
-int run_problem(mce_ctx* c, const Run& r) {
+// Everything of one problem up to the device->host copy of its result head, enqueued on the context's stream without
+// a host synchronisation (pageable host->device copies still wait for the stream, see the CUDA runtime).
+int enqueue_problem(mce_ctx* c, const Run& r, Pending& pd) {
     const mce_problem& p = *r.p;
     int rc = validate(&p, r.evidence);
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
+    pd.r = r;
+    const Sweep* sw = r.sweep;
     const bool devptr = (p.flags & MCE_FLAG_DEVICE_PTRS) != 0;
     const int f32 = (p.flags & MCE_FLAG_F32_SAMPLES) ? 1 : 0;   // query / ref are float32 arrays
     const size_t esz = f32 ? sizeof(float) : sizeof(double);
     const bool cross = p.ref != nullptr;
     const int d = p.d;
     const long long nq_all = p.n_query;
-    const long long n_ref = cross ? p.n_ref : nq_all;
-    const long long qb = p.q_begin, qe = (p.q_end == 0) ? nq_all : p.q_end;
+    long long smax = 0;
+    if (sw) {
+        // batch b = the first S_b rows of the query set; the largest batch bounds the search
+        if (!r.evidence || sw->nb < 1 || sw->nb > 4096 || !sw->rows || !sw->results)
+            return fail(MCE_ERR_ARG, "bad batch-size sweep arguments (1..4096 batches)");
+        if (p.q_begin != 0 || p.q_end != 0) return fail(MCE_ERR_ARG, "a batch-size sweep takes no query row range");
+        if (p.flags & (MCE_FLAG_DEVICE_PTRS | MCE_FLAG_EXACT_ONLY))
+            return fail(MCE_ERR_ARG, "a batch-size sweep takes host arrays and the filtered search");
+        for (int b = 0; b < sw->nb; ++b) {
+            if (sw->rows[b] < 1 || sw->rows[b] > nq_all)
+                return fail(MCE_ERR_ARG, "batch %d: %lld rows outside [1, n_query=%lld]", b, (long long)sw->rows[b], nq_all);
+            if (sw->results[b].dknn || sw->results[b].idx)
+                return fail(MCE_ERR_ARG, "batch %d: neighbour arrays are not returned by a sweep", b);
+            if (!sw->results[b].logE) return fail(MCE_ERR_ARG, "results[%d].logE is NULL", b);
+            if (sw->rows[b] > smax) smax = sw->rows[b];
+        }
+    }
+    const bool sweep_auto = sw && !cross;          // prefixes of one set: chunked filter pass + per-batch re-rank
+    const long long n_ref = cross ? p.n_ref : (sw ? smax : nq_all);
+    const long long qb = sw ? 0 : p.q_begin, qe = sw ? smax : ((p.q_end == 0) ? nq_all : p.q_end);
     const long long nq = qe - qb;
     const int kmax = p.kmax < 2 ? 2 : p.kmax;
 
@@ -224,12 +313,18 @@ int run_problem(mce_ctx* c, const Run& r) {
     if (n_ref - (cross ? 0 : 1) < K)
         return fail(MCE_ERR_ARG, "Expected n_neighbors <= n_samples_fit: %d neighbours from %lld reference rows", K,
                     n_ref - (cross ? 0 : 1));
+    if (sweep_auto)
+        for (int b = 0; b < sw->nb; ++b)
+            if (sw->rows[b] - 1 < K)
+                return fail(MCE_ERR_ARG, "Expected n_neighbors <= n_samples_fit: %d neighbours from the %lld rows of batch %d",
+                            K, (long long)sw->rows[b] - 1, b);
 
     int launches = 0;
-    CU(cudaEventRecord(c->ev[EV_START], st));
+    CU(cudaEventRecord(pd.ev0 ? pd.ev0 : c->ev[EV_START], st));
 
     // ---- inputs on the device ------------------------------------------------------------
     const void *dq = nullptr, *dr = nullptr;
+    const long long *dq_rows = nullptr, *dr_rows = nullptr;
     const double *dlogl = nullptr, *dw = nullptr;
     long long ldq = p.ld_query, ldr = p.ld_ref;
     if (devptr) {
@@ -259,10 +354,39 @@ int run_problem(mce_ctx* c, const Run& r) {
             *dptr = buf.p;
             return MCE_OK;
         };
-        rc = upload(c->xq, p.query, nq_all, p.ld_query, &dq, &ldq);
+        // with a row map the array is the base the samples are gathered from (burn-in / thinning / split on the
+        // device): the whole base goes up once, the covariance and whitening kernels follow the map as they load
+        const long long nq_up = p.query_rows ? p.n_query_base : ((sw && p.W) ? smax : nq_all);
+        rc = upload(c->xq, p.query, nq_up, p.ld_query, &dq, &ldq);
         if (rc) return rc;
         if (cross) {
-            rc = upload(c->xr, p.ref, n_ref, p.ld_ref, &dr, &ldr);
+            const bool same_base = p.query_rows && p.ref_rows && p.ref == p.query && p.ld_ref == p.ld_query &&
+                                   p.n_ref_base == p.n_query_base;
+            if (same_base) {      // the two halves of one split chain
+                dr = dq;
+                ldr = ldq;
+            } else {
+                rc = upload(c->xr, p.ref, p.ref_rows ? p.n_ref_base : n_ref, p.ld_ref, &dr, &ldr);
+                if (rc) return rc;
+            }
+        }
+        auto upload_rows = [&](DevBuf& buf, const int64_t* rows, long long n, long long n_base, const char* what,
+                               const long long** dptr) -> int {
+            for (long long i = 0; i < n; ++i)
+                if (rows[i] < 0 || rows[i] >= n_base)
+                    return fail(MCE_ERR_ARG, "%s[%lld]=%lld outside the %lld base rows", what, i, (long long)rows[i], n_base);
+            int rc2 = buf.ensure((size_t)n * 8);
+            if (rc2) return rc2;
+            CU(cudaMemcpyAsync(buf.p, rows, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+            *dptr = buf.as<long long>();
+            return MCE_OK;
+        };
+        if (p.query_rows) {
+            rc = upload_rows(c->rows_q, p.query_rows, nq_all, p.n_query_base, "query_rows", &dq_rows);
+            if (rc) return rc;
+        }
+        if (cross && p.ref_rows) {
+            rc = upload_rows(c->rows_r, p.ref_rows, n_ref, p.n_ref_base, "ref_rows", &dr_rows);
             if (rc) return rc;
         }
         if (r.evidence) {
@@ -290,8 +414,8 @@ int run_problem(mce_ctx* c, const Run& r) {
         rc = c->covpart.ensure((size_t)grid * (npairs > d ? npairs : d) * 8);
         if (rc) return rc;
         CovWorkspace ws{c->covpart.as<double>(), ds->mean, ds->W, &ds->logj, &ds->status};
-        Segment a{dq, nq_all, ldq, f32};
-        Segment b{cross ? dr : nullptr, cross ? n_ref : 0, ldr, f32};
+        Segment a{dq, nq_all, ldq, f32, dq_rows};
+        Segment b{cross ? dr : nullptr, cross ? n_ref : 0, ldr, f32, dr_rows};
         launch_covariance(a, b, d, ws, grid, st, &launches);
         dW = ds->W;
         dWr = ds->W;
@@ -323,14 +447,14 @@ int run_problem(mce_ctx* c, const Run& r) {
     if (rc) return rc;
     const double* yq_base;
     if (cross) {
-        launch_whiten(Segment{dr, n_ref, ldr, f32}, d, dWr, dmu, c->yr.as<double>(), c->tiles.as<float>(), &ds->rmax_bits, st,
+        launch_whiten(Segment{dr, n_ref, ldr, f32, dr_rows}, d, dWr, dmu, c->yr.as<double>(), c->tiles.as<float>(), &ds->rmax_bits, st,
                       &launches);
         rc = c->yq.ensure((size_t)nq * d * 8);
         if (rc) return rc;
-        launch_whiten(Segment{dq, nq_all, ldq, f32}.rows_from(qb, nq), d, dW, dmu, c->yq.as<double>(), nullptr, nullptr, st, &launches);
+        launch_whiten(Segment{dq, nq_all, ldq, f32, dq_rows}.rows_from(qb, nq), d, dW, dmu, c->yq.as<double>(), nullptr, nullptr, st, &launches);
         yq_base = c->yq.as<double>() - qb * d;
     } else {
-        launch_whiten(Segment{dq, nq_all, ldq, f32}, d, dW, dmu, c->yr.as<double>(), c->tiles.as<float>(), &ds->rmax_bits, st,
+        launch_whiten(Segment{dq, n_ref, ldq, f32, dq_rows}, d, dW, dmu, c->yr.as<double>(), c->tiles.as<float>(), &ds->rmax_bits, st,
                       &launches);
         yq_base = c->yr.as<double>();
     }
@@ -406,9 +530,47 @@ int run_problem(mce_ctx* c, const Run& r) {
     }
     const int nqblocks = (int)((nq + qpc - 1) / qpc);
     const long long nq_pad = (long long)nqblocks * qpc;
-    const long long slots = (long long)c->sm_count * ctas;
+    // several problems in flight (mce_evidence_batch): plan for this problem's share of the SMs
+    const int sm_eff = c->share > 1 ? (c->sm_count / c->share > 8 ? c->sm_count / c->share : 8) : c->sm_count;
+    const long long slots = (long long)sm_eff * ctas;
     int chunks = 1, nfull = nqblocks;
-    if (c->opt_chunks > 0) {
+    std::vector<int> chunk_tile0;      // sweep: chunk boundaries in tiles of the engine in use
+    std::vector<long long> sw_off, sw_rows, sw_edge;
+    std::vector<int> sw_nchunk;
+    if (sweep_auto) {
+        // Reference chunks end at the tile-aligned batch sizes: batch b merges the candidate lists of the chunks wholly
+        // inside [0, S_b) and scans the partial tile [edge_b, S_b) directly in the re-rank.
+        const int T = use_tc ? TC_TILE_REFS : TJ;
+        std::vector<int> bnd;
+        for (int b = 0; b < sw->nb; ++b)
+            if (sw->rows[b] < smax && sw->rows[b] / T > 0) bnd.push_back((int)(sw->rows[b] / T));
+        bnd.push_back(ftiles);
+        std::sort(bnd.begin(), bnd.end());
+        bnd.erase(std::unique(bnd.begin(), bnd.end()), bnd.end());
+        chunk_tile0.push_back(0);
+        for (int t : bnd) chunk_tile0.push_back(t);
+        chunks = (int)bnd.size();
+        nfull = 0;
+        long long off = 0;
+        for (int b = 0; b < sw->nb; ++b) {
+            const long long sb = sw->rows[b];
+            sw_off.push_back(off);
+            sw_rows.push_back(sb);
+            off += sb;
+            if (sb == smax) {
+                sw_nchunk.push_back(chunks);
+                sw_edge.push_back(sb);
+            } else {
+                const int tb = (int)(sb / T);
+                int nc = 0;
+                while (nc < chunks && chunk_tile0[nc + 1] <= tb) ++nc;
+                sw_nchunk.push_back(nc);
+                sw_edge.push_back((long long)tb * T);
+            }
+        }
+        sw_off.push_back(off);
+        if (off >= 0x7fffffffLL) return fail(MCE_ERR_ARG, "batch-size sweep: %lld rows in total exceed 2^31-1", off);
+    } else if (c->opt_chunks > 0) {
         chunks = c->opt_chunks;      // uniform split (tuning / tests)
         nfull = 0;
     } else if (c->opt_tail > 0) {
@@ -417,15 +579,18 @@ int run_problem(mce_ctx* c, const Run& r) {
     } else {
         // tensor-core engine: a pair costs about 1/100 cycle per SM whatever ndim is, a slow-path visit a few hundred
         // warp cycles, i.e. relatively far more than in the FFMA filter (a guess until it is calibrated on hardware)
-        const SplitPlan pl = plan_split(nqblocks, c->sm_count, qpc, ctas, n_ref, list_len, d, cfg.tq >= 4, max_chunks,
+        const SplitPlan pl = plan_split(nqblocks, sm_eff, qpc, ctas, n_ref, list_len, d, cfg.tq >= 4, max_chunks,
                                         use_tc ? 1500.0 : 0.0);
         chunks = pl.chunks;
         nfull = pl.nfull;
     }
-    if (chunks > ftiles) chunks = ftiles;
-    const int tiles_per_chunk = (ftiles + chunks - 1) / chunks;
-    chunks = (ftiles + tiles_per_chunk - 1) / tiles_per_chunk;
-    if (chunks == 1) nfull = nqblocks;
+    int tiles_per_chunk = ftiles;
+    if (!sweep_auto) {
+        if (chunks > ftiles) chunks = ftiles;
+        tiles_per_chunk = (ftiles + chunks - 1) / chunks;
+        chunks = (ftiles + tiles_per_chunk - 1) / tiles_per_chunk;
+        if (chunks == 1) nfull = nqblocks;
+    }
 
     // candidate planes: chunk 0 for every query, chunks 1.. only for the queries of the split blocks
     const long long tail_q0 = (long long)nfull * qpc;
@@ -435,8 +600,33 @@ int run_problem(mce_ctx* c, const Run& r) {
     if (rc) return rc;
     rc = c->cand_th.ensure(cand_elems * sizeof(float));
     if (rc) return rc;
-    rc = c->flagged.ensure((size_t)nq * sizeof(int));
+    const long long out_rows = sweep_auto ? sw_off.back() : nq;   // rows of the neighbour arrays
+    rc = c->flagged.ensure((size_t)out_rows * sizeof(int));
     if (rc) return rc;
+    // sweep metadata on the device: [off (nb+1) | rows (nb) | edge (nb)] long long, then [nchunk (nb) | chunk_tile0] int
+    const long long *d_sw_off = nullptr, *d_sw_rows = nullptr, *d_sw_edge = nullptr;
+    const int *d_sw_nchunk = nullptr, *d_chunk_tile0 = nullptr;
+    if (sweep_auto) {
+        const int nb = sw->nb;
+        const size_t nll = (size_t)3 * nb + 1, nint = (size_t)nb + chunk_tile0.size();
+        rc = c->sweep_meta.ensure(nll * 8 + nint * 4);
+        if (rc) return rc;
+        rc = c->hmeta.ensure(nll * 8 + nint * 4);
+        if (rc) return rc;
+        long long* hl = c->hmeta.as<long long>();
+        memcpy(hl, sw_off.data(), (size_t)(nb + 1) * 8);
+        memcpy(hl + nb + 1, sw_rows.data(), (size_t)nb * 8);
+        memcpy(hl + 2 * nb + 1, sw_edge.data(), (size_t)nb * 8);
+        int* hi = reinterpret_cast<int*>(hl + nll);
+        memcpy(hi, sw_nchunk.data(), (size_t)nb * 4);
+        memcpy(hi + nb, chunk_tile0.data(), chunk_tile0.size() * 4);
+        CU(cudaMemcpyAsync(c->sweep_meta.p, c->hmeta.p, nll * 8 + nint * 4, cudaMemcpyHostToDevice, st));
+        d_sw_off = c->sweep_meta.as<long long>();
+        d_sw_rows = d_sw_off + nb + 1;
+        d_sw_edge = d_sw_off + 2 * nb + 1;
+        d_sw_nchunk = reinterpret_cast<const int*>(d_sw_off + nll);
+        d_chunk_tile0 = d_sw_nchunk + nb;
+    }
 
     if (!exact_only) {
         FilterParams fp;
@@ -459,6 +649,7 @@ int run_problem(mce_ctx* c, const Run& r) {
         fp.nfull = nfull;
         fp.list_len = list_len;
         fp.d = d;
+        fp.chunk_tile0 = d_chunk_tile0;
         if (use_tc) {
             // Bound on |coarse - exact| per pair, e = slack_qr |q| Rmax + slack_rr Rmax^2: both operands are
             // truncated to TF32 (2^-10 relative each, 2^-9 (1 + 2^-10) on a product, summed with Cauchy-Schwarz),
@@ -508,7 +699,7 @@ int run_problem(mce_ctx* c, const Run& r) {
     if (devptr && user_dknn) {
         d_dknn = user_dknn;
     } else {
-        rc = c->dknn.ensure((size_t)nq * out_cols * 8);
+        rc = c->dknn.ensure((size_t)out_rows * out_cols * 8);
         if (rc) return rc;
         d_dknn = c->dknn.as<double>();
     }
@@ -516,7 +707,7 @@ int run_problem(mce_ctx* c, const Run& r) {
         if (devptr) {
             d_idx = reinterpret_cast<long long*>(user_idx);
         } else {
-            rc = c->idx.ensure((size_t)nq * out_cols * 8);
+            rc = c->idx.ensure((size_t)out_rows * out_cols * 8);
             if (rc) return rc;
             d_idx = c->idx.as<long long>();
         }
@@ -549,6 +740,12 @@ int run_problem(mce_ctx* c, const Run& r) {
     rp.out_col0 = out_col0;
     rp.write_self_col = write_self;
     rp.flag_all = exact_only ? 1 : 0;
+    rp.sweep_off = d_sw_off;
+    rp.sweep_rows = d_sw_rows;
+    rp.sweep_edge = d_sw_edge;
+    rp.sweep_nchunk = d_sw_nchunk;
+    rp.sweep_nb = sweep_auto ? sw->nb : 0;
+    rp.sweep_total = sweep_auto ? out_rows : 0;
     launch_rerank(rp, st, &launches);
     CU(cudaEventRecord(c->ev[EV_RERANK], st));
     const int exact_grid = c->sm_count * 4;
@@ -560,37 +757,87 @@ int run_problem(mce_ctx* c, const Run& r) {
     // ---- K4: epilogue -------------------------------------------------------------------------
     const int nk = kmax - 1;
     if (r.evidence) {
-        const int rgrid = reduce_grid_size(nq);
-        rc = c->redpart.ensure((size_t)rgrid * nk * 3 * 8);
-        if (rc) return rc;
         ReduceParams ep;
-        ep.dknn = d_dknn;
         ep.logl = dlogl;
         ep.weights = dw;
-        ep.block_partial = c->redpart.as<double>();
-        ep.out = ds->out;
-        ep.q_begin = qb;
-        ep.q_end = qe;
         ep.ld = out_cols;
         ep.col0 = out_col0;
         ep.first_nb = cross ? 2 : 1;
         ep.nk = nk;
         ep.d = d;
-        launch_reduce(ep, rgrid, st, &launches);
+        if (!sw) {
+            const int rgrid = reduce_grid_size(nq);
+            rc = c->redpart.ensure((size_t)rgrid * nk * 3 * 8);
+            if (rc) return rc;
+            ep.dknn = d_dknn;
+            ep.block_partial = c->redpart.as<double>();
+            ep.out = ds->out;
+            ep.q_begin = qb;
+            ep.q_end = qe;
+            launch_reduce(ep, rgrid, st, &launches);
+        } else {
+            // one reduction per batch size over its rows: rows [off_b, off_b + S_b) of the sweep's neighbour array
+            // (auto mode), or the first S_b rows of the one search against s2 (cross mode)
+            rc = c->redpart.ensure((size_t)reduce_grid_size(smax) * nk * 3 * 8);
+            if (rc) return rc;
+            rc = c->sweep_out.ensure((size_t)sw->nb * nk * 3 * 8);
+            if (rc) return rc;
+            for (int b = 0; b < sw->nb; ++b) {
+                const long long sb = sw->rows[b];
+                ep.dknn = d_dknn + (sweep_auto ? sw_off[b] : 0) * out_cols;
+                ep.block_partial = c->redpart.as<double>();
+                ep.out = c->sweep_out.as<double>() + (size_t)b * nk * 3;
+                ep.q_begin = 0;
+                ep.q_end = sb;
+                launch_reduce(ep, reduce_grid_size(sb), st, &launches);
+            }
+        }
     }
     CU(cudaEventRecord(c->ev[EV_REDUCE], st));
 
     // ---- results back ---------------------------------------------------------------------------
-    CU(cudaMemcpyAsync(c->hscal, ds, offsetof(DevScalars, mean), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(&c->hscal->status, &ds->status, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    DevScalars* hres = r.hres ? r.hres : c->hscal;
+    CU(cudaMemcpyAsync(hres, ds, DEV_HEAD_BYTES, cudaMemcpyDeviceToHost, st));
+    if (sw) {
+        rc = c->hres.ensure((size_t)sw->nb * nk * 3 * 8);
+        if (rc) return rc;
+        pd.h_sweep_out = c->hres.as<double>();
+        CU(cudaMemcpyAsync(pd.h_sweep_out, c->sweep_out.p, (size_t)sw->nb * nk * 3 * 8, cudaMemcpyDeviceToHost, st));
+    }
     if (!devptr) {
         if (user_dknn) CU(cudaMemcpyAsync(user_dknn, d_dknn, (size_t)nq * out_cols * 8, cudaMemcpyDeviceToHost, st));
         if (user_idx) CU(cudaMemcpyAsync(user_idx, d_idx, (size_t)nq * out_cols * 8, cudaMemcpyDeviceToHost, st));
     }
-    CU(cudaEventRecord(c->ev[EV_END], st));
-    CU(cudaStreamSynchronize(st));
-    CU(cudaGetLastError());
+    CU(cudaEventRecord(pd.ev1 ? pd.ev1 : c->ev[EV_END], st));
 
+    pd.use_tc = use_tc;
+    pd.exact_only = exact_only;
+    pd.cross = cross;
+    pd.d = d;
+    pd.nk = nk;
+    pd.launches = launches;
+    pd.nq_all = nq_all;
+    pd.nq = nq;
+    pd.n_ref = n_ref;
+    pd.cfg = cfg;
+    pd.chunks = chunks;
+    pd.list_len = list_len;
+    pd.nfull = nfull;
+    pd.nqblocks = nqblocks;
+    pd.smem = smem;
+    pd.ctas = ctas;
+    pd.hres = hres;
+    if (sw) pd.sweep_rows.assign(sw->rows, sw->rows + sw->nb);
+    return MCE_OK;
+}
+
+// After the stream has been synchronised: diagnostics, error state, statistics and the host arithmetic of the result.
+int complete_problem(mce_ctx* c, Pending& pd) {
+    const Run& r = pd.r;
+    const mce_problem& p = *r.p;
+    cudaStream_t st = c->stream;
+    const bool use_tc = pd.use_tc, exact_only = pd.exact_only;
+    const int d = pd.d, nk = pd.nk;
     if (use_tc && c->opt_tc_timeline && !c->opt_tc_check && !exact_only) {
         c->dbg_tc_dump.resize((size_t)TC_QUERIES * TC_TILE_REFS);
         CU(cudaMemcpy(c->dbg_tc_dump.data(), c->tc_dump.p, c->dbg_tc_dump.size() * sizeof(float), cudaMemcpyDeviceToHost));
@@ -612,7 +859,8 @@ int run_problem(mce_ctx* c, const Run& r) {
             return fail(MCE_ERR_INTERNAL, "tcgen05 filter: a %s wait made no progress for 0.5 s and gave up (a=0x%x b=0x%x block=%u); "
                         "results discarded", stuck[0] == 1u ? "barrier" : stuck[0] == 2u ? "queue-full" : "queue-slot", stuck[1], stuck[2], stuck[3]);
     }
-    if (c->hscal->status != 0)
+    const DevScalars* h = pd.hres;
+    if (h->status != 0)
         return fail(MCE_ERR_NOT_POSDEF,
                     "sample covariance of the %d selected parameters is not positive definite "
                     "(reference: negative eigenvalue warning, MCEvidence.py:867)", d);
@@ -621,43 +869,74 @@ int run_problem(mce_ctx* c, const Run& r) {
     memset(&sst, 0, sizeof(sst));
     float ms = 0.f;
     auto el = [&](int a, int b) { cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]); return (double)ms; };
-    sst.ms_total = el(EV_START, EV_END);
-    sst.ms_h2d = el(EV_START, EV_H2D);
-    sst.ms_cov = el(EV_H2D, EV_COV);
-    sst.ms_whiten = el(EV_COV, EV_WHITEN);
-    sst.ms_filter = el(EV_WHITEN, EV_FILTER);
-    sst.ms_rerank = el(EV_FILTER, EV_RERANK);
-    sst.ms_exact = el(EV_RERANK, EV_EXACT);
-    sst.ms_reduce = el(EV_EXACT, EV_REDUCE);
-    sst.ms_d2h = el(EV_REDUCE, EV_END);
-    sst.pairs = nq * n_ref;
-    sst.rows_rescanned = c->hscal->nflagged;
-    sst.launches = launches;
-    sst.filter_tq = cfg.tq;
-    sst.filter_tr = cfg.tr;
-    sst.filter_packed = cfg.packed;
-    sst.filter_mode = cfg.sync;
-    sst.ref_chunks = chunks;
-    sst.list_len = list_len;
-    sst.filter_grid = nfull + (nqblocks - nfull) * chunks;
-    sst.filter_smem = smem;
-    sst.filter_ctas_per_sm = ctas;
-    memcpy(&sst.rmax, &c->hscal->rmax_bits, 4);
+    if (pd.ev0) {   // batch lane: the lane's stage events belong to its last problem; only the total is per problem
+        cudaEventElapsedTime(&ms, pd.ev0, pd.ev1);
+        sst.ms_total = ms;
+    } else {
+        sst.ms_total = el(EV_START, EV_END);
+        sst.ms_h2d = el(EV_START, EV_H2D);
+        sst.ms_cov = el(EV_H2D, EV_COV);
+        sst.ms_whiten = el(EV_COV, EV_WHITEN);
+        sst.ms_filter = el(EV_WHITEN, EV_FILTER);
+        sst.ms_rerank = el(EV_FILTER, EV_RERANK);
+        sst.ms_exact = el(EV_RERANK, EV_EXACT);
+        sst.ms_reduce = el(EV_EXACT, EV_REDUCE);
+        sst.ms_d2h = el(EV_REDUCE, EV_END);
+    }
+    sst.pairs = pd.nq * pd.n_ref;
+    sst.rows_rescanned = h->nflagged;
+    sst.launches = pd.launches;
+    sst.filter_tq = pd.cfg.tq;
+    sst.filter_tr = pd.cfg.tr;
+    sst.filter_packed = pd.cfg.packed;
+    sst.filter_mode = pd.cfg.sync;
+    sst.ref_chunks = pd.chunks;
+    sst.list_len = pd.list_len;
+    sst.filter_grid = pd.nfull + (pd.nqblocks - pd.nfull) * pd.chunks;
+    sst.filter_smem = pd.smem;
+    sst.filter_ctas_per_sm = pd.ctas;
+    memcpy(&sst.rmax, &h->rmax_bits, 4);
 
-    if (r.evidence) {
+    if (r.sweep) {
+        for (int b = 0; b < r.sweep->nb; ++b) {
+            mce_result* res = &r.sweep->results[b];
+            const double* out = pd.h_sweep_out + (size_t)b * nk * 3;
+            res->stats = sst;
+            res->log_jacobian = h->logj;
+            if ((p.flags & MCE_FLAG_PARTIALS) && res->partials) memcpy(res->partials, out, (size_t)nk * 3 * 8);
+            // S = the rows of this batch, SumW = all of s1 (MCEvidence.py:1123-1131, 1126)
+            const int rc = mce_finalize(out, nk, d, pd.cross ? 1 : 0, pd.sweep_rows[b], p.log_sum_w, h->logj, p.log_prior_volume,
+                                        res->logE, res->var_logE);
+            if (rc) return rc;
+        }
+    } else if (r.evidence) {
         mce_result* res = r.res;
         res->stats = sst;
-        res->log_jacobian = c->hscal->logj;
-        if ((p.flags & MCE_FLAG_PARTIALS) && res->partials) memcpy(res->partials, c->hscal->out, (size_t)nk * 3 * 8);
+        res->log_jacobian = h->logj;
+        if ((p.flags & MCE_FLAG_PARTIALS) && res->partials) memcpy(res->partials, h->out, (size_t)nk * 3 * 8);
         if (res->logE) {
-            rc = mce_finalize(c->hscal->out, nk, d, cross ? 1 : 0, nq_all, p.log_sum_w, c->hscal->logj,
-                              p.log_prior_volume, res->logE, res->var_logE);
+            const int rc = mce_finalize(h->out, nk, d, pd.cross ? 1 : 0, pd.nq_all, p.log_sum_w, h->logj,
+                                        p.log_prior_volume, res->logE, res->var_logE);
             if (rc) return rc;
         }
     } else if (r.stats) {
         *r.stats = sst;
     }
     return MCE_OK;
+}
+
+// one problem on the context's own stream: enqueue, wait, complete
+int run_problem(mce_ctx* c, const Run& r) {
+    Pending pd;
+    int rc = enqueue_problem(c, r, pd);
+    if (rc) {
+        cudaStreamSynchronize(c->stream);   // nothing of a failed call stays in flight
+        cudaGetLastError();
+        return rc;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    return complete_problem(c, pd);
 }
 
 }  // namespace
@@ -720,11 +999,18 @@ int mce_ctx_create(int device, mce_ctx** out) {
 
 void mce_ctx_destroy(mce_ctx* c) {
     if (!c) return;
+    for (mce_ctx* l : c->lanes) mce_ctx_destroy(l);
+    c->lanes.clear();
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    c->ev_pool.clear();
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     DevBuf* bufs[] = {&c->xq, &c->xr, &c->logl, &c->w, &c->yr, &c->yq, &c->tiles, &c->tc_tiles, &c->tc_debug, &c->tc_dump, &c->cand_idx, &c->cand_th,
-                      &c->dknn, &c->idx, &c->flagged, &c->covpart, &c->redpart, &c->scal, &c->sink, &c->exact};
+                      &c->dknn, &c->idx, &c->flagged, &c->covpart, &c->redpart, &c->scal, &c->sink, &c->exact, &c->sweep_meta,
+                      &c->sweep_out, &c->rows_q, &c->rows_r};
     for (DevBuf* b : bufs) b->release();
+    c->hres.release();
+    c->hmeta.release();
     for (int i = 0; i < EV_COUNT; ++i)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->hscal) cudaFreeHost(c->hscal);
@@ -749,6 +1035,10 @@ int mce_ctx_set_option(mce_ctx* c, const char* name, int value) {
     else if (!strcmp(name, "list_margin")) c->opt_margin = value;
     else if (!strcmp(name, "filter_sync")) c->opt_sync = value;
     else if (!strcmp(name, "tail_chunks")) c->opt_tail = value;
+    else if (!strcmp(name, "batch_lanes")) {
+        if (value < 1 || value > 32) return fail(MCE_ERR_ARG, "batch_lanes must be in [1, 32]");
+        c->opt_lanes = value;
+    }
     else if (!strcmp(name, "filter_engine")) {
         if (value < 0 || value > 2) return fail(MCE_ERR_ARG, "filter_engine must be 0 (FFMA), 1 (tcgen05) or 2 (automatic)");
         c->opt_engine = value;
@@ -798,21 +1088,111 @@ int mce_evidence(mce_ctx* c, const mce_problem* problem, mce_result* result) {
     return run_problem(c, r);
 }
 
+// Independent problems (the (model, data, chain) loop of planck_mcevidence.py:306-359) overlap on up to "batch_lanes"
+// child contexts: each lane has its own stream and workspace, problems are dealt largest first and enqueued without
+// waiting for results; one synchronisation per lane at the end.  A problem is planned for its share of the SMs, so small
+// chains are not cut into many short units just to fill the GPU on their own.
 int mce_evidence_batch(mce_ctx* c, int n, const mce_problem* problems, mce_result* results) {
     if (!c) return fail(MCE_ERR_ARG, "ctx is NULL");
     if (n < 0 || (n > 0 && (!problems || !results))) return fail(MCE_ERR_ARG, "bad batch arguments");
     std::lock_guard<std::mutex> lk(c->mu);
-    for (int i = 0; i < n; ++i) {
+    for (int i = 0; i < n; ++i)
         if (!results[i].logE) return fail(MCE_ERR_ARG, "results[%d].logE is NULL", i);
+    if (n == 0) return MCE_OK;
+    auto named = [&](int i, int rc) {
+        char tmp[sizeof(g_err)];
+        snprintf(tmp, sizeof(tmp), "%s", g_err);
+        return fail(rc, "problem %d: %s", i, tmp);
+    };
+    const int nl = c->opt_lanes < n ? c->opt_lanes : n;
+    if (nl <= 1 || (problems[0].flags & MCE_FLAG_DEVICE_PTRS)) {
+        for (int i = 0; i < n; ++i) {
+            Run r{&problems[i], true, 0, nullptr, nullptr, &results[i], nullptr};
+            const int rc = run_problem(c, r);
+            if (rc) return named(i, rc);
+        }
+        return MCE_OK;
+    }
+    CU(cudaSetDevice(c->device));
+    while ((int)c->lanes.size() < nl) {
+        mce_ctx* l = nullptr;
+        const int rc = mce_ctx_create(c->device, &l);
+        if (rc) return rc;
+        c->lanes.push_back(l);
+    }
+    while ((int)c->ev_pool.size() < 2 * n) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        c->ev_pool.push_back(e);
+    }
+    int rc = c->hres.ensure((size_t)n * sizeof(DevScalars));
+    if (rc) return rc;
+    // largest first, round-robin over the lanes (the enqueue order interleaves the lanes)
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    auto cost = [&](int i) {
+        const mce_problem& q = problems[i];
+        return (double)q.n_query * (double)(q.ref ? q.n_ref : q.n_query);
+    };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost(a) > cost(b); });
+    for (int l = 0; l < nl; ++l) {
+        mce_ctx* lane = c->lanes[l];
+        lane->opt_tq = c->opt_tq; lane->opt_tr = c->opt_tr; lane->opt_packed = c->opt_packed; lane->opt_chunks = c->opt_chunks;
+        lane->opt_margin = c->opt_margin; lane->opt_sync = c->opt_sync; lane->opt_tail = c->opt_tail;
+        lane->opt_engine = c->opt_engine; lane->opt_tc_slack = c->opt_tc_slack; lane->opt_tc_stages = c->opt_tc_stages;
+        lane->opt_tc_mma_warps = c->opt_tc_mma_warps;
+        lane->share = nl;
+    }
+    std::vector<Pending> pend(n);
+    int failed = -1, failed_rc = 0;
+    for (int j = 0; j < n && failed < 0; ++j) {
+        const int i = order[j];
+        mce_ctx* lane = c->lanes[j % nl];
         Run r{&problems[i], true, 0, nullptr, nullptr, &results[i], nullptr};
-        const int rc = run_problem(c, r);
+        r.hres = c->hres.as<DevScalars>() + i;
+        r.batch_lane = true;
+        pend[i].ev0 = c->ev_pool[2 * i];
+        pend[i].ev1 = c->ev_pool[2 * i + 1];
+        rc = enqueue_problem(lane, r, pend[i]);
         if (rc) {
-            char tmp[sizeof(g_err)];
-            snprintf(tmp, sizeof(tmp), "%s", g_err);
-            return fail(rc, "problem %d: %s", i, tmp);
+            failed = i;
+            failed_rc = rc;
+            named(i, rc);
         }
     }
+    char first_err[sizeof(g_err)];
+    snprintf(first_err, sizeof(first_err), "%s", g_err);
+    for (int l = 0; l < nl; ++l) {
+        const cudaError_t e = cudaStreamSynchronize(c->lanes[l]->stream);
+        if (e != cudaSuccess && failed < 0) {
+            failed = n;
+            failed_rc = MCE_ERR_CUDA;
+            snprintf(first_err, sizeof(first_err), "batch lane %d: %s", l, cudaGetErrorString(e));
+        }
+    }
+    cudaGetLastError();
+    if (failed >= 0) return fail(failed_rc, "%s", first_err);
+    for (int j = 0; j < n; ++j) {      // in enqueue order: the first failing problem is reported
+        const int i = order[j];
+        rc = complete_problem(c->lanes[j % nl], pend[i]);
+        if (rc) return named(i, rc);
+    }
     return MCE_OK;
+}
+
+// Batch-size sweep (MCEvidence.py:808-840, 1039-1045): the evidence of the first batch_rows[b] rows of the query set for
+// every b, from one upload, one whitening and ONE pass of the filter over the largest batch.
+int mce_evidence_sweep(mce_ctx* c, const mce_problem* problem, int nbatch, const int64_t* batch_rows, mce_result* results) {
+    if (!c) return fail(MCE_ERR_ARG, "ctx is NULL");
+    if (!problem || nbatch < 1 || !batch_rows || !results) return fail(MCE_ERR_ARG, "bad sweep arguments");
+    std::lock_guard<std::mutex> lk(c->mu);
+    Sweep sw;
+    sw.nb = nbatch;
+    sw.rows = batch_rows;
+    sw.results = results;
+    Run r{problem, true, 0, nullptr, nullptr, &results[0], nullptr};
+    r.sweep = &sw;
+    return run_problem(c, r);
 }
 
 int mce_knn(mce_ctx* c, const mce_problem* problem, int n_neighbors, double* dknn, int64_t* idx, mce_stats* stats) {

@@ -29,13 +29,17 @@ struct Segment {            // one strided sample array, float64 or float32 (MCE
     long long n;
     long long ld;           // row stride in elements
     int f32;
+    const long long* rows;  // optional row map (burn-in / thinning / split applied on the device): row r = x[rows[r]]
     __host__ __device__ __forceinline__ double at(long long r, int c) const {
-        return f32 ? (double)static_cast<const float*>(x)[r * ld + c] : static_cast<const double*>(x)[r * ld + c];
+        const long long rr = rows ? rows[r] : r;
+        return f32 ? (double)static_cast<const float*>(x)[rr * ld + c] : static_cast<const double*>(x)[rr * ld + c];
     }
     __host__ __device__ __forceinline__ Segment rows_from(long long r0, long long count) const {
         Segment s = *this;
-        s.x = f32 ? static_cast<const void*>(static_cast<const float*>(x) + r0 * ld)
-                  : static_cast<const void*>(static_cast<const double*>(x) + r0 * ld);
+        if (rows) s.rows = rows + r0;
+        else
+            s.x = f32 ? static_cast<const void*>(static_cast<const float*>(x) + r0 * ld)
+                      : static_cast<const void*>(static_cast<const double*>(x) + r0 * ld);
         s.n = count;
         return s;
     }
@@ -80,7 +84,19 @@ struct FilterParams {
                              // blocks [nfull, nqblocks) are split into ref_chunks units each
     int list_len;
     int d;
+    const int* chunk_tile0;  // batch-size sweep: ref_chunks + 1 tile indices, chunk r = tiles [chunk_tile0[r], chunk_tile0[r+1])
+                             // (the prefix boundaries of MCEvidence.py:1039-1045); nullptr: uniform tiles_per_chunk
 };
+// first and one-past-last tile of reference chunk r of a split query block
+__device__ __forceinline__ void chunk_tile_range(const FilterParams& p, int r, int* t0, int* t1) {
+    if (p.chunk_tile0) {
+        *t0 = p.chunk_tile0[r];
+        *t1 = p.chunk_tile0[r + 1];
+    } else {
+        *t0 = r * p.tiles_per_chunk;
+        *t1 = min(*t0 + p.tiles_per_chunk, p.ntiles);
+    }
+}
 // element offsets into the candidate buffers (shared by the filter and the re-rank)
 __host__ __device__ __forceinline__ long long cand_idx_offset(int r, int e, long long ql, int list_len, long long nq_pad,
                                                               long long ntail_pad, long long tail_q0) {
@@ -154,7 +170,24 @@ struct RerankParams {
     int out_ld, out_col0;    // output row stride and first column (1 when a synthetic self column is kept)
     int write_self_col;      // write (0.0, own index) into column 0
     int flag_all;            // MCE_FLAG_EXACT_ONLY: flag every row
+    // Batch-size sweep (MCEvidence.py:1039-1045; sweep_nb == 0: one problem).  Batch b searches queries [0, S_b) among
+    // references [0, S_b) (auto mode).  One filter pass over the largest batch with reference chunks cut at the tile
+    // aligned batch sizes serves every batch: batch b merges the candidates of the chunks wholly inside [0, S_b) and
+    // scans the references of the partial tile [sweep_edge[b], S_b) directly.  Output row of (b, query j) =
+    // sweep_off[b] + j; that row id is also what `flagged` holds.
+    const long long* sweep_off;    // [nb + 1]
+    const long long* sweep_rows;   // [nb]  S_b
+    const long long* sweep_edge;   // [nb]  first reference not covered by the chunks of batch b (tile aligned, <= S_b)
+    const int* sweep_nchunk;       // [nb]  chunks wholly inside [0, S_b)
+    int sweep_nb;
+    long long sweep_total;         // = sweep_off[nb] (host copy: the launch size)
 };
+// sweep row id -> (batch, query)
+__device__ __forceinline__ int sweep_batch_of(const RerankParams& p, long long t) {
+    int b = 0;
+    while (b + 1 < p.sweep_nb && t >= p.sweep_off[b + 1]) ++b;
+    return b;
+}
 void launch_rerank(const RerankParams& p, cudaStream_t st, int* launches);
 size_t exact_scratch_bytes(int grid);
 void launch_exact_rescan(const RerankParams& p, int grid, void* scratch, cudaStream_t st, int* launches);

@@ -129,8 +129,7 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
         const int rem = p.nqblocks - p.nfull;
         rchunk = v / rem;
         qblock = p.nfull + v % rem;
-        t0 = rchunk * p.tiles_per_chunk;
-        t1 = min(t0 + p.tiles_per_chunk, p.ntiles);
+        chunk_tile_range(p, rchunk, &t0, &t1);
     }
     const long long ql0 = (long long)qblock * (NT * TQ) + tid;  // local id of this thread's first query
     const long long nq = p.q_end - p.q_begin;

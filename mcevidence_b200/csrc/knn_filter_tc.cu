@@ -353,8 +353,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
         const int rem = p.nqblocks - p.nfull;
         rchunk = v / rem;
         qblock = p.nfull + v % rem;
-        t0 = rchunk * p.tiles_per_chunk;
-        t1 = min(t0 + p.tiles_per_chunk, p.ntiles);
+        chunk_tile_range(p, rchunk, &t0, &t1);
     }
     const int nt = t1 - t0;
     const long long nq = p.q_end - p.q_begin;

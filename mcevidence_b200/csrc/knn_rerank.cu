@@ -95,12 +95,13 @@ struct TopList {
     }
 };
 
-__device__ __forceinline__ void write_row(const RerankParams& p, long long ql, const TopList& top) {
-    double* drow = p.dknn + ql * p.out_ld;
-    long long* irow = p.idx ? p.idx + ql * p.out_ld : nullptr;
+// `row` = output row, `self` = reference index written into the synthetic self column
+__device__ __forceinline__ void write_row(const RerankParams& p, long long row, long long self, const TopList& top) {
+    double* drow = p.dknn + row * p.out_ld;
+    long long* irow = p.idx ? p.idx + row * p.out_ld : nullptr;
     if (p.write_self_col) {
         drow[0] = 0.0;
-        if (irow) irow[0] = p.q_begin + ql + p.self_offset;
+        if (irow) irow[0] = self;
     }
 #pragma unroll
     for (int i = 0; i < KCAP; ++i) {
@@ -112,27 +113,54 @@ __device__ __forceinline__ void write_row(const RerankParams& p, long long ql, c
 }
 
 __global__ void __launch_bounds__(128) rerank_kernel(const RerankParams p) {
-    const long long ql = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long nq = p.q_end - p.q_begin;
-    if (ql >= nq || *p.status != 0) return;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool sweep = p.sweep_nb > 0;
+    const long long nrows = sweep ? p.sweep_off[p.sweep_nb] : p.q_end - p.q_begin;
+    if (t >= nrows || *p.status != 0) return;
     if (p.flag_all) {
-        p.flagged[ql] = (int)ql;
-        if (ql == 0) *p.nflagged = (int)nq;
+        p.flagged[t] = (int)t;
+        if (t == 0) *p.nflagged = (int)nrows;
         return;
+    }
+    // (batch, query) of this row; a single problem is batch 0 with every chunk
+    long long ql = t;
+    int nchunks;
+    long long edge = 0, edge_end = 0;
+    if (sweep) {
+        const int b = sweep_batch_of(p, t);
+        ql = t - p.sweep_off[b];
+        nchunks = p.sweep_nchunk[b];
+        edge = p.sweep_edge[b];
+        edge_end = p.sweep_rows[b];
+    } else {
+        nchunks = ql < p.nfull_queries ? 1 : p.ref_chunks;
     }
     const int d = p.d;
     const double* q = p.yq + (p.q_begin + ql) * d;
+    const long long self = p.q_begin + ql + p.self_offset;
     TopList top;
     top.init();
     float thmax = -CUDART_INF_F;
-    const int nchunks = ql < p.nfull_queries ? 1 : p.ref_chunks;
-    for (int r = 0; r < nchunks; ++r) {
-        thmax = fmaxf(thmax, p.cand_th[cand_th_offset(r, ql, p.nq_pad, p.ntail_pad, p.tail_q0)]);
-        for (int e = 0; e < p.list_len; ++e) {
-            const int id = p.cand_idx[cand_idx_offset(r, e, ql, p.list_len, p.nq_pad, p.ntail_pad, p.tail_q0)];
+    for (int r = 0; r < nchunks; ++r) thmax = fmaxf(thmax, p.cand_th[cand_th_offset(r, ql, p.nq_pad, p.ntail_pad, p.tail_q0)]);
+    // one candidate stream (a single insertion site keeps the sorted list in registers): the filter's lists chunk by
+    // chunk, then -- sweep only -- the references of the partial tile behind the last whole chunk
+    const long long nlist = (long long)nchunks * p.list_len;
+    const long long ncand = nlist + (edge_end - edge);
+    int r = 0, e = 0;
+    for (long long i = 0; i < ncand; ++i) {
+        long long id;
+        if (i < nlist) {
+            id = p.cand_idx[cand_idx_offset(r, e, ql, p.list_len, p.nq_pad, p.ntail_pad, p.tail_q0)];
+            if (++e == p.list_len) {
+                e = 0;
+                ++r;
+            }
             if (id < 0) continue;
-            top.push(sq_dist_seq(q, p.yr + (long long)id * d, d), id);
+        } else {
+            id = edge + (i - nlist);
+            if (p.self_exclude && id == self) continue;
         }
+        top.push(sq_dist_seq(q, p.yr + id * d, d), id);
     }
     double qn2 = 0.0;
     for (int c = 0; c < d; ++c) qn2 += q[c] * q[c];
@@ -141,10 +169,10 @@ __global__ void __launch_bounds__(128) rerank_kernel(const RerankParams p) {
     const double eps = 1.0625 * u * ((d + 2) * sqrt(qn2) * rmax + 0.5 * (d + 1) * rmax * rmax);
     const double bound = qn2 - 2.0 * ((double)thmax + eps);
     const bool ok = (thmax == -CUDART_INF_F) || (top.dist[p.k - 1] < bound);
-    write_row(p, ql, top);
+    write_row(p, t, self, top);
     if (!ok) {
         const int pos = atomicAdd(p.nflagged, 1);
-        p.flagged[pos] = (int)ql;
+        p.flagged[pos] = (int)t;
     }
 }
 
@@ -175,18 +203,24 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_rescan_kernel(const Reran
     const int d = p.d;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nseg = exact_segments(nfl, gridDim.x);
-    const long long seg_len = (p.n_ref + nseg - 1) / nseg;
     for (long long item = blockIdx.x; item < (long long)nfl * nseg; item += gridDim.x) {
         const int f = (int)(item / nseg);
         const int seg = (int)(item % nseg);
-        const long long ql = p.flagged[f];
+        const long long row = p.flagged[f];
+        long long ql = row, n_ref = p.n_ref;
+        if (p.sweep_nb > 0) {
+            const int b = sweep_batch_of(p, row);
+            ql = row - p.sweep_off[b];
+            n_ref = p.sweep_rows[b];
+        }
+        const long long seg_len = (n_ref + nseg - 1) / nseg;
         const double* qg = p.yq + (p.q_begin + ql) * d;
         __syncthreads();
         for (int c = threadIdx.x; c < d; c += EXACT_THREADS) sq[c] = qg[c];
         __syncthreads();
         const long long self = p.self_exclude ? p.q_begin + ql + p.self_offset : -1;
         const long long j_lo = seg * seg_len;
-        const long long j_hi = min(p.n_ref, j_lo + seg_len);
+        const long long j_hi = min(n_ref, j_lo + seg_len);
         TopList top;
         top.init();
         for (long long j = j_lo + threadIdx.x; j < j_hi; j += EXACT_THREADS) {
@@ -225,7 +259,7 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_rescan_kernel(const Reran
         }
         if (threadIdx.x == 0) {
             if (nseg == 1) {
-                write_row(p, ql, res);
+                write_row(p, row, p.q_begin + ql + p.self_offset, res);
             } else {
 #pragma unroll
                 for (int i = 0; i < KCAP; ++i) {
@@ -254,13 +288,15 @@ __global__ void __launch_bounds__(128) exact_merge_kernel(const RerankParams p, 
             if (dd < CUDART_INF) top.push(dd, scratch_i[item * KCAP + i]);
         }
     }
-    write_row(p, p.flagged[f], top);
+    const long long row = p.flagged[f];
+    const long long ql = p.sweep_nb > 0 ? row - p.sweep_off[sweep_batch_of(p, row)] : row;
+    write_row(p, row, p.q_begin + ql + p.self_offset, top);
 }
 
 }  // namespace
 
 void launch_rerank(const RerankParams& p, cudaStream_t st, int* launches) {
-    const long long nq = p.q_end - p.q_begin;
+    const long long nq = p.sweep_nb > 0 ? p.sweep_total : p.q_end - p.q_begin;
     if (nq <= 0) return;
     const int threads = 128;
     rerank_kernel<<<(unsigned)((nq + threads - 1) / threads), threads, 0, st>>>(p);

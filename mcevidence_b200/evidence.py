@@ -189,6 +189,20 @@ class MCEvidence(object):
                 s = self.diagonalise_chain(s, e_vec, e_val)
         return s, lnp, w, {'J': jac, 'eVec': e_vec, 'eVal': e_val}
 
+    def _device_views(self):
+        """``[(base, rows) of s1, (base, rows) of s2]`` when the partitions are still row maps of the chain (files read
+        with thinning and / or a split) and the context can follow them, else None."""
+        ctx = _lib.default_context(self.device)
+        if not getattr(ctx, 'supports_row_maps', False):
+            return None
+        v1 = self.gd.data['s1'].device_view()
+        if v1 is None:
+            return None
+        if not self.split:
+            return [v1]
+        v2 = self.gd.data['s2'].device_view()
+        return None if v2 is None else [v1, v2]
+
     @staticmethod
     def _reference_factor(cs):
         """The reference's whitening matrix ``eVec / sqrt(eVal)`` for an explicit-W call."""
@@ -220,11 +234,49 @@ class MCEvidence(object):
 
         mle = np.zeros((self.nbatch, kmax))
         var = np.zeros((self.nbatch, kmax))
-        s1_all, _, _ = self.gd.arrays('s1')
         full = self.brange is None
         sum_w = np.sum(self.gd.data['s1'].adjusted_weights)                   # MCEvidence.py:1126
         cov_all = None
-        for ipow, nsample in zip(self.idbatch, self.nchain):
+        batches = list(zip(self.idbatch, self.nchain))
+        if not full and covtype == 'all' and not rand and len(batches) > 1 and hasattr(ctx, 'evidence_sweep'):
+            # N4: every batch is a prefix of s1 whitened with the covariance of ALL samples (MCEvidence.py:1034-1045),
+            # so one upload, one whitening and one pass of the filter over the largest prefix serve all of them
+            s1_all, logl, weight = self.gd.arrays('s1')
+            samples = s1_all[:, 0:ndim]
+            if pos_lnp:
+                logl = -logl                                                  # MCEvidence.py:1060
+            samples2 = self.get_samples(0, prewhiten=False, name='s2')[0] if self.split else None
+            cov_all = self.get_covariance()
+            cov_mu = self.gd.all_sample_arrays()[0][:, 0:ndim].mean(axis=0)
+            rows = [int(nsample[0]) for _, nsample in batches]
+            outs = ctx.evidence_sweep(samples, logl, weight, kmax, rows, ref=samples2, ndim=ndim,
+                                      W=self._reference_factor(cov_all), mu=cov_mu, log_jacobian=math.log(cov_all['J']),
+                                      log_sum_w=math.log(sum_w), log_prior_volume=log_pv)
+            for (ipow, _), out in zip(batches, outs):
+                mle[ipow, 1:] = out['logE']
+                var[ipow, 1:] = out['var_logE']
+            self.last_stats = outs[-1]['stats']
+            batches = []
+        views = self._device_views() if (full and covtype == 'all' and batches) else None
+        if views is not None:
+            # N2: burn-in / thinning / split stay row maps of the chain; the device gathers the rows as it loads
+            # (MCEvidence.py:174-249, 350-391, 417-445 decide WHICH rows on the host, with numpy's global RNG)
+            d1 = self.gd.data['s1']
+            logl = d1.loglikes if pos_lnp else -d1.loglikes                   # MCEvidence.py:399, 1060
+            kw = {'query_rows': views[0][1]}
+            ref = None
+            if self.split:
+                ref, kw['ref_rows'] = views[1][0][:, 0:ndim], views[1][1]
+                self.logger.info('using XMCEvidence. NN distance is estimated using nsamples=(%s, %s)'
+                                 % (len(views[0][1]), len(views[1][1])))
+            out = ctx.evidence(views[0][0][:, 0:ndim], logl, d1.weights, kmax, ref=ref, ndim=ndim,
+                               log_sum_w=math.log(sum_w), log_prior_volume=log_pv, **kw)
+            ipow = batches[0][0]
+            mle[ipow, 1:] = out['logE']
+            var[ipow, 1:] = out['var_logE']
+            self.last_stats = out['stats']
+            batches = []
+        for ipow, nsample in batches:
             s_n = int(nsample[0])
             samples, logl, weight, _ = self.get_samples(s_n, istart=0, rand=rand, prewhiten=False, name='s1')
             if pos_lnp:

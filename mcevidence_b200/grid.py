@@ -29,26 +29,15 @@ def assign_largest_first(sizes, world):
     return buckets
 
 
-_stream_contexts = {}
-
-
-def _contexts(device, n):
-    """``n`` independent contexts (stream + workspace each) on ``device`` for overlapping small problems."""
-    have = _stream_contexts.setdefault(device, [])
-    while len(have) < n:
-        have.append(_lib.Context(device))
-    return have[:n]
-
-
-def evidence_many(chains, kmax=2, ndim=None, priorvolume=1.0, device=0, ctx=None, group=None, nstreams=4):
+def evidence_many(chains, kmax=2, ndim=None, priorvolume=1.0, device=0, ctx=None, group=None, nstreams=8):
     """Auto-mode log-evidence of every chain in ``chains`` (arrays ``[weight, -logL, theta...]``).
 
     ``ndim`` / ``priorvolume`` may be scalars or per-chain sequences.  Single process: all chains run
     on ``device``.  With an initialised ``torch.distributed`` group every rank must pass the same
     list; rank r computes its share and all ranks return the full list of ``logE`` arrays.
-    A rank's share is further dealt over ``nstreams`` contexts of the same GPU, each driven by its own
-    host thread through one ``mce_evidence_batch`` call (ctypes releases the GIL), so that the kernels of
-    small chains -- which cannot fill 148 SMs on their own -- overlap.
+    A rank's share goes to the library in ONE ``mce_evidence_batch`` call, which overlaps the problems on
+    ``nstreams`` internal streams ("batch_lanes"), so that the kernels of small chains -- which cannot fill
+    148 SMs on their own -- run side by side.
     """
     n = len(chains)
     ndims = [ndim] * n if (ndim is None or np.isscalar(ndim)) else list(ndim)
@@ -65,20 +54,9 @@ def evidence_many(chains, kmax=2, ndim=None, priorvolume=1.0, device=0, ctx=None
         nd = c.shape[1] - 2 if ndims[i] is None else int(ndims[i])
         probs.append({'query': c[:, 2:], 'logl': -c[:, 1], 'weights': c[:, 0], 'kmax': kmax, 'ndim': nd,
                       'log_sum_w': math.log(np.sum(c[:, 0])), 'log_prior_volume': math.log(pvs[i])})
-    nstreams = max(1, min(int(nstreams), len(probs) // 4)) if ctx is None else 1
-    if nstreams <= 1:
-        ctx = ctx or _lib.default_context(device)
-        outs = ctx.evidence_batch(probs) if probs else []          # one C call: mce_evidence_batch
-    else:
-        from concurrent.futures import ThreadPoolExecutor
-        lanes = assign_largest_first([len(p['weights']) for p in probs], nstreams)
-        ctxs = _contexts(device, nstreams)
-        with ThreadPoolExecutor(max_workers=nstreams) as pool:
-            parts = list(pool.map(lambda cl: cl[0].evidence_batch([probs[j] for j in cl[1]]), zip(ctxs, lanes)))
-        outs = [None] * len(probs)
-        for lane, part in zip(lanes, parts):
-            for j, o in zip(lane, part):
-                outs[j] = o
+    ctx = ctx or _lib.default_context(device)
+    ctx.set_option('batch_lanes', max(1, min(int(nstreams), 32)))
+    outs = ctx.evidence_batch(probs) if probs else []              # one C call: mce_evidence_batch
     local = {i: (o['logE'], o['var_logE'], o['stats']['ms_total']) for i, o in zip(mine, outs)}
     if world > 1:
         gathered = [None] * world

@@ -85,12 +85,19 @@ class OracleContext:
     """Stand-in for _lib.Context.evidence built on the CPU oracle.  TEST-ONLY: lets the CPU suite
     exercise the Python glue of MCEvidence.evidence() (argument plumbing, covtype branches, batching)."""
 
+    supports_row_maps = True
+
     def evidence(self, query, logl, weights, kmax, ref=None, ndim=None, W=None, W_ref=None, mu=None,
-                 log_jacobian=0.0, log_sum_w=0.0, log_prior_volume=0.0, q_range=None, **_):
+                 log_jacobian=0.0, log_sum_w=0.0, log_prior_volume=0.0, q_range=None, query_rows=None, ref_rows=None,
+                 **_):
         from oracle import mce_oracle as O
         kmax = max(2, int(kmax))
         q = np.asarray(query, dtype=np.float64)[:, :ndim]
         r = None if ref is None else np.asarray(ref, dtype=np.float64)[:, :ndim]
+        if query_rows is not None:          # row maps (N2): the gather the device does as it loads
+            q = q[np.asarray(query_rows)]
+        if ref_rows is not None:
+            r = r[np.asarray(ref_rows)]
         if W is None:
             cs = O.covariance_stats(q if r is None else np.concatenate((q, r)))
             yq = O.whiten(q, cs['eVec'], cs['eVal'])
@@ -110,3 +117,8 @@ class OracleContext:
         mle, var = O.evidence_from_dknn_log(dknn, np.asarray(logl), np.asarray(weights), ndim, kmax, k0,
                                             math.exp(log_sum_w), log_jacobian, log_prior_volume)
         return {'logE': mle[1:], 'var_logE': var[1:], 'log_jacobian': log_jacobian, 'stats': {}}
+
+    def evidence_sweep(self, query, logl, weights, kmax, batch_rows, ref=None, **kw):
+        """Prefix by prefix with the same explicit whitening: what mce_evidence_sweep must reproduce."""
+        return [self.evidence(np.asarray(query)[:int(n)], np.asarray(logl)[:int(n)], np.asarray(weights)[:int(n)], kmax,
+                              ref=ref, **kw) for n in batch_rows]

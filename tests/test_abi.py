@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     assert {'mce_evidence', 'mce_knn', 'mce_evidence_batch', 'mce_ctx_create', 'mce_finalize'} <= set(names)
     for n in names:
         assert hasattr(lib, n), 'symbol %s declared in the header is not exported' % n
-    assert lib.mce_version() == 1
+    assert lib.mce_version() == 2
 
 
 def test_struct_layout_matches_header(tmp_path):

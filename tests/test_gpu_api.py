@@ -143,3 +143,104 @@ def test_planck_grid_driver(tmp_path):
     want = O.evidence(c[:, 2:], -c[:, 1], c[:, 0], 6, 2, adjusted_weights=aw, knn='brute')
     assert abs(df.loc['base', 'chain1'] - want[0]) < 1e-8
     assert np.isclose(df.loc['base', 'Err_lnE_k1'], df.loc['base', ['chain1', 'chain2']].std() / np.sqrt(2.0))
+
+
+@pytest.mark.parametrize('engine', [0, 1])
+@pytest.mark.parametrize('cross', [False, True])
+def test_batch_size_sweep_is_bit_identical(engine, cross):
+    """N4: mce_evidence_sweep (one upload, one whitening, one filter pass cut at the tile-aligned batch sizes) against
+    one mce_evidence call per prefix with the same explicit whitening -- bit for bit (MCEvidence.py:1039-1045)."""
+    from mcevidence_b200 import _lib
+    n, d, kmax = 5300, 6, 4
+    c, _ = gaussian_chain(n + (2100 if cross else 0), d, seed=71, mean_shift=0.2)
+    s, logl, w = c[:n, 2:], -c[:n, 1], c[:n, 0]
+    ref = c[n:, 2:] if cross else None
+    cov = np.cov(c[:, 2:].T)
+    W = np.linalg.inv(np.linalg.cholesky(cov)).T.copy()
+    mu = c[:, 2:].mean(axis=0)
+    logj = 0.5 * np.linalg.slogdet(cov)[1]
+    rows = [5300, 37, 1000, 1000, 2511, 256, 4097, 5299, 130]      # unsorted, repeated, below one tile, tile aligned
+    ctx = _lib.Context(0)
+    ctx.set_option('filter_engine', engine)
+    kw = dict(ndim=d, W=W, mu=mu, log_jacobian=logj, log_sum_w=math.log(w.sum()), log_prior_volume=0.3)
+    got = ctx.evidence_sweep(s, logl, w, kmax, rows, ref=ref, **kw)
+    assert got[0]['stats']['filter_mode'] == (16 if engine else got[0]['stats']['filter_mode'])
+    for nb, g in zip(rows, got):
+        want = ctx.evidence(s[:nb], logl[:nb], w[:nb], kmax, ref=ref, **kw)
+        np.testing.assert_array_equal(g['logE'], want['logE'])
+        np.testing.assert_array_equal(g['var_logE'], want['var_logE'])
+    # W == NULL: the covariance of ALL rows (covtype='all'), not of the prefix
+    got2 = ctx.evidence_sweep(s, logl, w, kmax, [900, n], ref=ref, ndim=d, log_sum_w=math.log(w.sum()))
+    full = ctx.evidence(s, logl, w, kmax, ref=ref, ndim=d, log_sum_w=math.log(w.sum()))
+    np.testing.assert_array_equal(got2[1]['logE'], full['logE'])
+    want = O.evidence(s[:900], logl[:900], w[:900], d, kmax, s2=ref, knn='brute', cov_from=c[:, 2:] if cross else s,
+                      sum_w=w.sum())
+    assert np.abs(got2[0]['logE'] - want).max() < 1e-9
+    with pytest.raises(_lib.MCEError):
+        ctx.evidence_sweep(s, logl, w, kmax, [3], ref=None if not cross else ref[:2], **kw)   # fewer rows than neighbours
+    ctx.close()
+
+
+def test_batch_lanes_match_single_calls():
+    """mce_evidence_batch overlaps problems on internal streams: results equal n mce_evidence calls bit for bit,
+    whatever the number of lanes, and a failing problem is named."""
+    from mcevidence_b200 import _lib
+    shapes = [(1475, 6), (9000, 7), (3000, 8), (2200, 9), (4000, 7), (700, 6), (15000, 6), (5100, 9), (800, 7), (12000, 8)]
+    chains = [gaussian_chain(n, d, seed=130 + i, integer_weights=True, inflate=1.0, nextra=3)[0]
+              for i, (n, d) in enumerate(shapes)]
+    probs = [{'query': c[:, 2:], 'logl': -c[:, 1], 'weights': c[:, 0], 'kmax': 3, 'ndim': d,
+              'log_sum_w': math.log(c[:, 0].sum()), 'log_prior_volume': 0.1 * i}
+             for i, (c, (_, d)) in enumerate(zip(chains, shapes))]
+    ctx = _lib.Context(0)
+    single = [ctx.evidence(p['query'], p['logl'], p['weights'], 3, ndim=p['ndim'], log_sum_w=p['log_sum_w'],
+                           log_prior_volume=p['log_prior_volume']) for p in probs]
+    for lanes in (1, 3, 8):
+        ctx.set_option('batch_lanes', lanes)
+        for rep in range(2):                       # second pass: warm workspaces
+            outs = ctx.evidence_batch(probs)
+            for o, s1 in zip(outs, single):
+                np.testing.assert_array_equal(o['logE'], s1['logE'])
+                np.testing.assert_array_equal(o['var_logE'], s1['var_logE'])
+                assert o['log_jacobian'] == s1['log_jacobian']
+    bad = np.column_stack((np.ones(50), np.zeros(50), np.ones((50, 2))))
+    probs.insert(4, {'query': bad[:, 2:], 'logl': -bad[:, 1], 'weights': bad[:, 0], 'kmax': 3, 'ndim': 2})
+    with pytest.raises(_lib.MCEError, match='problem 4'):
+        ctx.evidence_batch(probs)
+    ctx.close()
+
+
+def test_row_maps_gather_on_the_device():
+    """N2: burn-in / thinning / split as row maps of the chain (query_rows / ref_rows), gathered by the covariance and
+    whitening kernels as they load -- bit-identical to the host-gathered arrays (MCEvidence.py:174-249, 417-445)."""
+    from mcevidence_b200 import _lib
+    rng = np.random.default_rng(5)
+    c, _ = gaussian_chain(9000, 7, seed=77, nextra=4, mean_shift=0.3)
+    base = c[1200:, 2:]                                   # burn-in = a view of the chain; rows keep the nuisance columns
+    nb = base.shape[0]
+    keep = np.flatnonzero(rng.poisson(0.6, size=nb) > 0)            # thinning keeps a subset ...
+    perm = rng.permutation(len(keep))
+    r1, r2 = keep[perm[:len(keep) // 2]], keep[np.sort(perm[len(keep) // 2:])]   # ... the split draws s1 unordered
+    w = rng.integers(1, 5, size=nb).astype(float)
+    logl = -c[1200:, 1]
+    ctx = _lib.Context(0)
+    kw = dict(ndim=7, log_prior_volume=0.2)
+    # auto mode
+    a = ctx.evidence(base, logl[keep], w[keep], 3, query_rows=keep, log_sum_w=math.log(w[keep].sum()), want_knn=True, **kw)
+    b = ctx.evidence(base[keep], logl[keep], w[keep], 3, log_sum_w=math.log(w[keep].sum()), want_knn=True, **kw)
+    np.testing.assert_array_equal(a['logE'], b['logE'])
+    np.testing.assert_array_equal(a['dknn'], b['dknn'])
+    np.testing.assert_array_equal(a['idx'], b['idx'])
+    assert a['log_jacobian'] == b['log_jacobian']
+    # cross mode, both halves rows of the same base (uploaded once), and of different bases
+    a = ctx.evidence(base, logl[r1], w[r1], 3, ref=base, query_rows=r1, ref_rows=r2, log_sum_w=1.0, **kw)
+    b = ctx.evidence(base[r1], logl[r1], w[r1], 3, ref=base[r2], log_sum_w=1.0, **kw)
+    np.testing.assert_array_equal(a['logE'], b['logE'])
+    other = np.ascontiguousarray(base[:, :7])
+    a2 = ctx.evidence(base, logl[r1], w[r1], 3, ref=other, query_rows=r1, ref_rows=r2, log_sum_w=1.0, **kw)
+    np.testing.assert_array_equal(a2['logE'], b['logE'])
+    # sweep over prefixes of the mapped rows
+    sw = ctx.evidence_sweep(base, logl[keep], w[keep], 3, [700, len(keep)], query_rows=keep, log_sum_w=0.5, **kw)
+    np.testing.assert_array_equal(sw[1]['logE'], ctx.evidence(base[keep], logl[keep], w[keep], 3, log_sum_w=0.5, **kw)['logE'])
+    with pytest.raises(_lib.MCEError, match='query_rows'):
+        ctx.evidence(base, logl[:3], w[:3], 2, query_rows=[0, nb, 1], ndim=7)
+    ctx.close()

@@ -23,7 +23,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--kind', default='AllChains')
 ap.add_argument('--cpu-cells', type=int, default=6)
 ap.add_argument('--reps', type=int, default=3)
-ap.add_argument('--nstreams', type=int, default=4)
+ap.add_argument('--nstreams', type=int, default=8)
 a = ap.parse_args()
 rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
 if world > 1:
