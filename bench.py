@@ -40,12 +40,21 @@ WORKLOADS = {
     'cfg5': (16000000, 20, 8, False, 'cfg5: N=1.6e7 d=20 kmax=8 auto (scaling run)'),
     'cfg5s': (2000000, 20, 8, False, 'cfg5 shape at N=2e6 d=20 kmax=8 auto'),
     'small': (100000, 10, 4, False, 'N=1e5 d=10 kmax=4 auto'),
+    # BASELINE cfg1: one CosmoMC root of the Planck grid -- 4 chain files of ~6.7k rows, 30 % burn-in, the 6 cosmological
+    # parameters of the base model out of 10 sampled columns, integer weights, kmax=2 (`MCEvidence.py <root> -k 2 -b 0.3`)
+    'cfg1': (4 * 4690, 6, 2, False, 'cfg1: Planck-shaped base-model root, 4 chains x 6.7k rows after 30% burn-in, ndim=6 of 10 columns, kmax=2'),
 }
+# BASELINE cfg4: every (model, data) cell of planck_fullgrid_R2/AllChains as one batch of independent problems
+GRID_WORKLOADS = {'cfg4': ('AllChains', 'cfg4: 175 (model, data) cells of planck_fullgrid_R2/AllChains, synthetic chains of the '
+                                        'tabulated (ndim, N), kmax=2, one mce_evidence_batch per step'),
+                  'cfg4s': ('SingleChains', 'cfg4 per-chain variant: 700 chains of planck_fullgrid_R2/SingleChains, kmax=2')}
 FP32_PEAK_THEORETICAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.4: SMs x lanes x 2 FLOP x max clock
 # dram__bytes_read.sum + dram__bytes_write.sum of one K2 launch from the ncu --set full capture of this command
 # (profiles/r01_filter_ncu_raw_final.csv: 148.7 MB read + 31.2 MB written; algorithmic: 44 MB tiles + 80 MB
 # queries + ~24 MB candidate lists -- the reference set is streamed from L2, not from HBM)
-NCU_DRAM_BYTES_PER_LAUNCH = {('cfg2', 1, False): 179.9e6}   # (workload, gpus, tcgen05 engine?)
+# tcgen05 engine (profiles/r02_tc_filter_ncu_raw_cfg2.csv): 670.4 MB read + 32.0 MB written; algorithmic: 64 MB image +
+# 80 MB queries + ~25 MB candidate lists -- the image is re-read from HBM when it falls out of L2 between query blocks
+NCU_DRAM_BYTES_PER_LAUNCH = {('cfg2', 1, False): 179.9e6, ('cfg2', 1, True): 702.3e6}   # (workload, gpus, tcgen05 engine?)
 METRIC = 'knn_pair_dists_per_s'
 UNIT = 'pair-dists/s'
 
@@ -53,6 +62,10 @@ UNIT = 'pair-dists/s'
 def make_workload(name, seed=0):
     from mcevidence_b200.synthetic import gaussian_chain
     n, d, kmax, cross, desc = WORKLOADS[name]
+    if name == 'cfg1':
+        chain, info = gaussian_chain(n, d, seed=seed, nextra=4, integer_weights=True, inflate=1.0, mean_shift=0.3)
+        return dict(s1=chain[:, 2:], s2=None, logl=-chain[:, 1], w=np.ascontiguousarray(chain[:, 0]), d=d, kmax=kmax,
+                    cross=False, desc=desc, lnZ=info['lnZ'])
     chain, info = gaussian_chain(n * (2 if cross else 1), d, seed=seed)
     s = np.ascontiguousarray(chain[:, 2:])
     logl, w = -chain[:, 1], np.ascontiguousarray(chain[:, 0])
@@ -263,6 +276,191 @@ def run_reference_arm(args, rank, world):
     return 0
 
 
+
+# ---------------------------------------------------------------------------------------------
+def run_grid_workload(args, rank, world, local_rank):
+    """cfg4: the whole Planck grid as ONE batch of independent auto-mode problems per step (planck_mcevidence.py:306-359).
+    `value` = sum of the cells' pair distances / device time of mce_evidence_batch with every chain resident in HBM;
+    `e2e` = the same batch from host arrays (grid.evidence_many); with N > 1 ranks the cells are dealt largest first
+    over the GPUs and no data-path collective is involved.  --impl reference: the unmodified reference cell by cell on
+    the host cores (a bounded sample of cells, scaled by pair count)."""
+    kind, desc = GRID_WORKLOADS[args.workload]
+    shapes = json.load(open(os.path.join(ROOT, 'mcevidence_b200', 'planck_grid_shapes.json')))[kind]
+    cells = [(nd, n) for (_, _, nd, ns) in shapes for n in ns]
+    from mcevidence_b200.synthetic import gaussian_chain
+    pairs_total = float(sum(float(n) ** 2 for _, n in cells))
+    config = {'workload': desc, 'cells': len(cells), 'rows': int(sum(n for _, n in cells)), 'pairs': pairs_total,
+              'ndim': '6-9', 'kmax': 2, 'mode': 'auto',
+              'parallelism': 'our arm: cells dealt largest-first over %d GPU(s), up to 8 problems in flight per GPU; reference arm: '
+                             'cell by cell, sklearn n_jobs=-1 on the host cores of rank 0' % max(1, world),
+              'l2': 'our arm: 512 MiB memset between timed steps (not timed)'}
+
+    def make(i):
+        nd, n = cells[i]
+        return gaussian_chain(n, nd, seed=i, inflate=1.0, integer_weights=True, nextra=3)[0]
+
+    def cpu_cells(target_s):
+        """The unmodified reference on a spread of cells until ~target_s seconds are spent; returns (seconds, pairs, n)."""
+        from oracle import ref_loader
+        import logging
+        order = np.argsort([-n for _, n in cells])
+        pick = [int(order[i]) for i in np.linspace(0, len(cells) - 1, 12).astype(int)]
+        R = ref_loader.load() if ref_loader.available() else None
+        t_sum, p_sum, done = 0.0, 0.0, 0
+        for i in pick:
+            c = make(i)
+            t0 = time.perf_counter()
+            if R is not None:
+                logging.disable(logging.CRITICAL)
+                try:
+                    R.MCEvidence([c], kmax=2, ndim=cells[i][0], verbose=0).evidence(nproc=-1)
+                finally:
+                    logging.disable(logging.NOTSET)
+            else:
+                from oracle import mce_oracle as O
+                O.evidence(c[:, 2:], -c[:, 1], c[:, 0], cells[i][0], 2, knn='sklearn', scalar_loop=True)
+            t_sum += time.perf_counter() - t0
+            p_sum += float(cells[i][1]) ** 2
+            done += 1
+            if t_sum > target_s:
+                break
+        return t_sum, p_sum, done, 'reference' if R is not None else 'port'
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        hi = host_info()
+        ts = []
+        for _ in range(max(1, args.steps)):
+            t_sum, p_sum, done, kind_ = cpu_cells(min(25.0, 200.0 / max(1, args.steps + 1)))
+            ts.append(t_sum)
+        # the kd-tree cost per cell is ~N^1.3, not N^2: scale the sample by sum(N^1.3), which favours the reference
+        w_all = float(sum(float(n) ** 1.3 for _, n in cells))
+        order = np.argsort([-n for _, n in cells])
+        pick = [int(order[i]) for i in np.linspace(0, len(cells) - 1, 12).astype(int)][:done]
+        w_s = float(sum(float(cells[i][1]) ** 1.3 for i in pick))
+        t_full = float(np.mean(ts)) * w_all / w_s
+        val = pairs_total / t_full
+        sample = ('%s MCEvidence([chain], kmax=2, ndim).evidence(nproc=-1) on %d of the %d cells (a spread over sizes), %.2f s; '
+                  'scaled to the whole grid by sum N^1.3 (kd_tree law): %.1f s per grid EXTRAPOLATED' % (
+                      'unmodified reference (oracle/_ref)' if kind_ == 'reference' else 'oracle port of', done, len(cells),
+                      float(np.mean(ts)), t_full))
+        print(json.dumps({'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
+                          'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * float(np.mean(ts)),
+                          'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                          'config': config, 'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': hi['cores'], 'kind': kind_,
+                                                             'sample': sample, 'cpu_model': hi['cpu_model']},
+                          'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                          'extrapolated': True, 's_per_grid': t_full, 'gpu_launches': 0}), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from mcevidence_b200 import _lib
+    from mcevidence_b200.grid import assign_largest_first, evidence_many
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'
+        dist.init_process_group('nccl', device_id=device)
+    ctx = _lib.default_context(local_rank)
+    ctx.set_option('batch_lanes', 8)
+    chains = [make(i) for i in range(len(cells))]
+    ndims = [nd for nd, _ in cells]
+    mine = assign_largest_first([n for _, n in cells], world)[rank]
+    # resident copies of this rank's cells: parameter columns contiguous, logL and weights as vectors
+    res, probs = [], []
+    for i in mine:
+        c = chains[i]
+        s = torch.from_numpy(np.ascontiguousarray(c[:, 2:2 + ndims[i]])).to(device)
+        ll = torch.from_numpy(np.ascontiguousarray(-c[:, 1])).to(device)
+        w = torch.from_numpy(np.ascontiguousarray(c[:, 0])).to(device)
+        res.append((s, ll, w))
+        probs.append({'query_ptr': s.data_ptr(), 'n_query': len(c), 'ld_query': ndims[i], 'logl_ptr': ll.data_ptr(),
+                      'weights_ptr': w.data_ptr(), 'ndim': ndims[i], 'kmax': 2, 'log_sum_w': math.log(c[:, 0].sum())})
+    torch.cuda.synchronize(device)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=device)
+    stream = torch.cuda.current_stream(device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for _ in range(args.warmup):
+        outs = ctx.evidence_batch_device(probs) if probs else []
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t_ms, launches = 0.0, 0
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)        # the batch runs on the library's own lanes: bracket it with a device-wide wait
+        t0 = time.perf_counter()
+        outs = ctx.evidence_batch_device(probs) if probs else []
+        torch.cuda.synchronize(device)
+        t_ms += 1e3 * (time.perf_counter() - t0)
+        launches += sum(o['stats']['launches'] for o in outs)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    tmax = torch.tensor([t_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    t_ms = float(tmax.item())
+    value = args.steps * pairs_total / (t_ms * 1e-3)
+    # e2e: host arrays in, logE out
+    for _ in range(2):
+        evidence_many(chains, kmax=2, ndim=ndims, device=local_rank)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loge, var, _ms = evidence_many(chains, kmax=2, ndim=ndims, device=local_rank)
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    te = float(te.item())
+    if rank == 0:
+        flop = float(sum(3.0 * nd * float(n) ** 2 for nd, n in cells))
+        h2d = int(sum(n * (nd + 3) + 2 * n for nd, n in cells)) * 8
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': t_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+                'dtype': 'f32 filter, f64 re-rank/reduce', 'data': 'synthetic', 'config': config,
+                'e2e': {'value': args.steps * pairs_total / te, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+                        'd2h_bytes_per_step': len(cells) * 8 * 8, 's_per_grid': te / args.steps},
+                'gpu_launches': launches, 'clocks': clocks,
+                'roofline': {'bound': 'fp32_fma', 'achieved': args.steps * flop / (t_ms * 1e-3) / 1e12,
+                             'peak': FP32_PEAK_THEORETICAL_TFLOPS, 'unit': 'TFLOP/s',
+                             'frac': args.steps * flop / (t_ms * 1e-3) / 1e12 / FP32_PEAK_THEORETICAL_TFLOPS, 'traffic': None,
+                             'kernel': 'whole batch (covariance, whitening, filter, re-rank, reduction of every cell; the filter '
+                                       'kernels of up to 8 cells overlap, so no single launch can be singled out)',
+                             'note': 'algorithmic 3 d FLOP per pair summed over the cells / wall time of the resident batch, '
+                                     'against the theoretical FP32 FMA peak'},
+                's_per_grid': t_ms * 1e-3 / args.steps, 'logE_first_cells': [float(x[0]) for x in loge[:4]]}
+        if world == 1 and not args.no_cpu_baseline:
+            t_sum, p_sum, done, kind_ = cpu_cells(args.cpu_seconds)
+            hi = host_info()
+            w_all = float(sum(float(n) ** 1.3 for _, n in cells))
+            order = np.argsort([-n for _, n in cells])
+            pick = [int(order[i]) for i in np.linspace(0, len(cells) - 1, 12).astype(int)][:done]
+            t_full = t_sum * w_all / float(sum(float(cells[i][1]) ** 1.3 for i in pick))
+            line['cpu_baseline'] = {'value': pairs_total / t_full, 'unit': UNIT, 'cores': hi['cores'], 'kind': kind_,
+                                    'sample': '%d of %d cells in %.2f s, scaled by sum N^1.3 to %.1f s per grid EXTRAPOLATED' % (
+                                        done, len(cells), t_sum, t_full), 'cpu_model': hi['cpu_model'], 's_per_grid': t_full}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 # ---------------------------------------------------------------------------------------------
 def _measured_tf32_peak():
     """TF32 dense peak for the roofline of the tcgen05 engine: half of the measured bf16 figure of
@@ -282,7 +480,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS) + sorted(GRID_WORKLOADS))
     ap.add_argument('--filter-engine', default=None, choices=['ffma', 'tc', 'auto'],
                     help="K2 engine: 'ffma' (FP32 FMA pipe), 'tc' (tcgen05 tensor-core filter) or 'auto' (chosen per problem, "
                          "the library default); not given = the library default or MCE_FILTER_ENGINE")
@@ -300,6 +498,8 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.workload in GRID_WORKLOADS:
+        return run_grid_workload(args, rank, world, local_rank)
     if args.impl == 'reference':
         return run_reference_arm(args, rank, world)
 
@@ -342,7 +542,7 @@ def main():
         return t
     host = {}
     if rank == 0:
-        host = {'samples': pinned(wl['s1']), 'logl': pinned(wl['logl']), 'weights': pinned(wl['w'])}
+        host = {'samples': pinned(np.ascontiguousarray(wl['s1'][:, :wl['d']])), 'logl': pinned(wl['logl']), 'weights': pinned(wl['w'])}
         if cross:
             host['ref'] = pinned(wl['s2'])
     res = {}

@@ -152,7 +152,8 @@ int  mce_ctx_set_stream(mce_ctx *ctx, void *cuda_stream);
    bit 1: descriptor version field 0), "tc_stages" (shared-memory ring depth 2..8, -1 = as many as fit),
    "tc_mma_warps" (1 or 2 warps issuing the MMAs, default 2), "tc_timeline" (ndim 7..14: record the hand-over
    times of CTA 0's first 1024 tiles, read back as "tc_dump"), "tc_perf_mode" (ndim 7..14, timing experiments whose
-   results are garbage: 1 = the epilogue skips the TMEM loads, 2 = loads without the threshold test). */
+   results are garbage: 1 = the epilogue skips the TMEM loads, 2 = loads without the threshold test, 3 = loads and
+   threshold test but nothing ever passes, i.e. the scan without a single hit). */
 int  mce_ctx_set_option(mce_ctx *ctx, const char *name, int value);
 /* Diagnostics of the last call on this context: "tc_check_ratio" (worst |coarse - exact| / allowance seen by a
    "tc_check" run; must stay below 1), "tc_check_pairs" (pairs compared, modulo 2^32), "filter_engine". */
@@ -175,6 +176,24 @@ int  mce_evidence_batch(mce_ctx *ctx, int n, const mce_problem *problems, mce_re
    merges the candidates of the ranges inside its prefix in the FP64 re-rank.  Each result equals the mce_evidence call
    on the prefix with the same explicit W / mu, bit for bit.  q_begin/q_end must be 0; dknn/idx are not returned. */
 int  mce_evidence_sweep(mce_ctx *ctx, const mce_problem *problem, int nbatch, const int64_t *batch_rows, mce_result *results);
+
+/* Device group: the GPUs of one box driven from ONE process, one host thread per device (the multi-GPU form of the
+   entry points above).  device_ids == NULL: devices 0..n_devices-1; n_devices <= 0: all.
+   mce_group_evidence shards the query rows over the devices: the sample arrays are uploaded once to the first device
+   and sent to the others with ncclBroadcast over NVLink (NCCL is bound with dlopen("libnccl.so.2"); when it cannot be
+   loaded, or MCE_GROUP_NO_NCCL=1, every device uploads the host arrays itself), every device whitens the whole
+   reference set and searches its block of rows, and the 3 (kmax-1) partial sums per device -- already in this
+   process's host memory -- are combined with mce_combine_partials.  mce_group_evidence_batch deals independent
+   problems largest-first over the devices (chain-per-GPU, planck_mcevidence.py:149-160) and runs each share as one
+   mce_evidence_batch.  Host-array problems only. */
+typedef struct mce_group mce_group;
+int  mce_group_create(int n_devices, const int *device_ids, mce_group **out);
+void mce_group_destroy(mce_group *group);
+int  mce_group_size(const mce_group *group);
+int  mce_group_uses_nccl(const mce_group *group);
+int  mce_group_set_option(mce_group *group, const char *name, int value);
+int  mce_group_evidence(mce_group *group, const mce_problem *problem, mce_result *result);
+int  mce_group_evidence_batch(mce_group *group, int n, const mce_problem *problems, mce_result *results);
 
 /* k nearest neighbours with sklearn's contract: dknn/idx are (q_end-q_begin, n_neighbors), ascending.
    Auto mode (ref == NULL): column 0 is the row itself at distance 0, as when the reference queries the

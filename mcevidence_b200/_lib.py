@@ -97,6 +97,14 @@ def load_library():
         lib.mce_evidence_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(Problem), C.POINTER(Result)]
         lib.mce_evidence_sweep.argtypes = [C.c_void_p, C.POINTER(Problem), C.c_int, c_int64_p, C.POINTER(Result)]
         lib.mce_knn.argtypes = [C.c_void_p, C.POINTER(Problem), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Stats)]
+        lib.mce_group_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
+        lib.mce_group_destroy.argtypes = [C.c_void_p]
+        lib.mce_group_destroy.restype = None
+        lib.mce_group_size.argtypes = [C.c_void_p]
+        lib.mce_group_uses_nccl.argtypes = [C.c_void_p]
+        lib.mce_group_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        lib.mce_group_evidence.argtypes = [C.c_void_p, C.POINTER(Problem), C.POINTER(Result)]
+        lib.mce_group_evidence_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(Problem), C.POINTER(Result)]
         lib.mce_combine_partials.argtypes = [C.c_int, C.c_int, c_double_p, c_double_p]
         lib.mce_finalize.argtypes = [c_double_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_double,
                                      C.c_double, c_double_p, c_double_p]
@@ -319,6 +327,30 @@ class Context:
             o['stats'] = rarr[b].stats.as_dict()
         return outs
 
+    def evidence_batch_device(self, problems):
+        """``mce_evidence_batch`` on DEVICE pointers: a list of dicts with ``query_ptr, n_query, ld_query, logl_ptr,
+        weights_ptr, ndim, kmax`` (auto mode) and optionally ``log_sum_w, log_prior_volume``; the arrays live on this
+        context's device (resident-input benchmark of the chain grid).  Returns a list of result dicts."""
+        n = len(problems)
+        parr = (Problem * n)()
+        rarr = (Result * n)()
+        outs = []
+        for i, kw in enumerate(problems):
+            p = parr[i]
+            p.query, p.n_query, p.ld_query = int(kw['query_ptr']), int(kw['n_query']), int(kw['ld_query'])
+            p.logl, p.weights = int(kw['logl_ptr']), int(kw['weights_ptr'])
+            p.d, p.kmax, p.flags = int(kw['ndim']), int(kw['kmax']), FLAG_DEVICE_PTRS
+            p.log_sum_w, p.log_prior_volume = float(kw.get('log_sum_w', 0.0)), float(kw.get('log_prior_volume', 0.0))
+            kk = max(2, int(kw['kmax']))
+            loge, var = np.empty(kk - 1), np.empty(kk - 1)
+            rarr[i].logE, rarr[i].var_logE = _ptr(loge), _ptr(var)
+            outs.append({'logE': loge, 'var_logE': var})
+        _check(self._lib, self._lib.mce_evidence_batch(self._h, n, parr, rarr))
+        for i, o in enumerate(outs):
+            o['log_jacobian'] = rarr[i].log_jacobian
+            o['stats'] = rarr[i].stats.as_dict()
+        return outs
+
     def knn(self, query, n_neighbors, ref=None, ndim=None, W=None, W_ref=None, mu=None, q_range=None,
             exact_only=False, identity=False, query_rows=None, ref_rows=None):
         """``mce_knn``: ``(dknn, idx, stats)`` with sklearn's ``kneighbors`` contract.
@@ -394,6 +426,87 @@ def combine_partials(parts):
     out = np.empty((nk, 3))
     _check(lib, lib.mce_combine_partials(nparts, nk, parts.ctypes.data_as(c_double_p), out.ctypes.data_as(c_double_p)))
     return out
+
+
+class Group:
+    """``mce_group``: the GPUs of one box driven from this one process, one host thread per device inside the library
+    (row-sharded :meth:`evidence`, chain-per-GPU :meth:`evidence_batch`).  ``devices``: a count, a list of ids, or None
+    for every device."""
+
+    def __init__(self, devices=None):
+        self._lib = load_library()
+        h = C.c_void_p()
+        if devices is None:
+            n, ids = 0, None
+        elif isinstance(devices, int):
+            n, ids = int(devices), None
+        else:
+            devs = [int(x) for x in devices]
+            n, ids = len(devs), (C.c_int * len(devs))(*devs)
+        _check(self._lib, self._lib.mce_group_create(n, ids, C.byref(h)))
+        self._h = h
+        self._helper = Context.__new__(Context)      # for _problem(): argument marshalling only, no device handle
+        self._helper._lib, self._helper._h = self._lib, None
+
+    @property
+    def size(self):
+        return int(self._lib.mce_group_size(self._h))
+
+    @property
+    def uses_nccl(self):
+        return bool(self._lib.mce_group_uses_nccl(self._h))
+
+    def set_option(self, name, value):
+        _check(self._lib, self._lib.mce_group_set_option(self._h, name.encode(), int(value)))
+
+    def close(self):
+        if self._h is not None:
+            self._lib.mce_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def evidence(self, query, logl, weights, kmax, ref=None, ndim=None, W=None, W_ref=None, mu=None, log_jacobian=0.0,
+                 log_sum_w=0.0, log_prior_volume=0.0, want_partials=False):
+        """``mce_group_evidence``: query rows sharded over the devices; same result dict as :meth:`Context.evidence`."""
+        keep = []
+        p, _ = self._helper._problem(query, ref, logl, weights, ndim, kmax, W, W_ref, mu, log_jacobian, log_sum_w,
+                                     log_prior_volume, None, FLAG_PARTIALS if want_partials else 0, keep)
+        kk = max(2, int(kmax))
+        r = Result()
+        out = {'logE': np.empty(kk - 1), 'var_logE': np.empty(kk - 1)}
+        r.logE, r.var_logE = _ptr(out['logE']), _ptr(out['var_logE'])
+        if want_partials:
+            out['partials'] = np.empty((kk - 1, 3))
+            r.partials = _ptr(out['partials'])
+        _check(self._lib, self._lib.mce_group_evidence(self._h, C.byref(p), C.byref(r)))
+        out.update({'log_jacobian': r.log_jacobian, 'stats': r.stats.as_dict()})
+        return out
+
+    def evidence_batch(self, problems):
+        """``mce_group_evidence_batch``: independent problems dealt largest-first over the devices."""
+        n = len(problems)
+        keep, outs = [], []
+        parr = (Problem * n)()
+        rarr = (Result * n)()
+        for i, kw in enumerate(problems):
+            p, _ = self._helper._problem(kw['query'], kw.get('ref'), kw['logl'], kw['weights'], kw.get('ndim'), kw['kmax'],
+                                         kw.get('W'), kw.get('W_ref'), kw.get('mu'), kw.get('log_jacobian', 0.0),
+                                         kw.get('log_sum_w', 0.0), kw.get('log_prior_volume', 0.0), None, 0, keep)
+            parr[i] = p
+            kk = max(2, int(kw['kmax']))
+            loge, var = np.empty(kk - 1), np.empty(kk - 1)
+            rarr[i].logE, rarr[i].var_logE = _ptr(loge), _ptr(var)
+            outs.append({'logE': loge, 'var_logE': var})
+        _check(self._lib, self._lib.mce_group_evidence_batch(self._h, n, parr, rarr))
+        for i, o in enumerate(outs):
+            o['log_jacobian'] = rarr[i].log_jacobian
+            o['stats'] = rarr[i].stats.as_dict()
+        return outs
 
 
 def finalize(partials, ndim, cross, n_query_total, log_sum_w, log_jacobian, log_prior_volume):

@@ -10,9 +10,14 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <mutex>
+#include <thread>
 #include <new>
+#include <string>
 #include <vector>
 
 using namespace mce;
@@ -1033,7 +1038,10 @@ int mce_ctx_set_option(mce_ctx* c, const char* name, int value) {
     else if (!strcmp(name, "filter_packed")) c->opt_packed = value;
     else if (!strcmp(name, "ref_chunks")) c->opt_chunks = value;
     else if (!strcmp(name, "list_margin")) c->opt_margin = value;
-    else if (!strcmp(name, "filter_sync")) c->opt_sync = value;
+    else if (!strcmp(name, "filter_sync")) {
+        if (value == 0) return fail(MCE_ERR_ARG, "filter_sync 0 (free-running warps) is no longer built: use 1, 2 or 3, or -1 for automatic");
+        c->opt_sync = value;
+    }
     else if (!strcmp(name, "tail_chunks")) c->opt_tail = value;
     else if (!strcmp(name, "batch_lanes")) {
         if (value < 1 || value > 32) return fail(MCE_ERR_ARG, "batch_lanes must be in [1, 32]");
@@ -1047,7 +1055,7 @@ int mce_ctx_set_option(mce_ctx* c, const char* name, int value) {
     else if (!strcmp(name, "tc_stages")) c->opt_tc_stages = value;
     else if (!strcmp(name, "tc_timeline")) c->opt_tc_timeline = value != 0;
     else if (!strcmp(name, "tc_mma_warps")) c->opt_tc_mma_warps = value == 1 ? 1 : 2;
-    else if (!strcmp(name, "tc_perf_mode")) c->opt_tc_perf = (value == 1 || value == 2) ? value : 0;
+    else if (!strcmp(name, "tc_perf_mode")) c->opt_tc_perf = (value >= 1 && value <= 3) ? value : 0;
     else if (!strcmp(name, "tc_slack_percent")) {
         if (value < 1) return fail(MCE_ERR_ARG, "tc_slack_percent must be positive");
         c->opt_tc_slack = value;
@@ -1105,7 +1113,7 @@ int mce_evidence_batch(mce_ctx* c, int n, const mce_problem* problems, mce_resul
         return fail(rc, "problem %d: %s", i, tmp);
     };
     const int nl = c->opt_lanes < n ? c->opt_lanes : n;
-    if (nl <= 1 || (problems[0].flags & MCE_FLAG_DEVICE_PTRS)) {
+    if (nl <= 1) {
         for (int i = 0; i < n; ++i) {
             Run r{&problems[i], true, 0, nullptr, nullptr, &results[i], nullptr};
             const int rc = run_problem(c, r);
@@ -1298,6 +1306,272 @@ int mce_unit_peak(mce_ctx* c, int unit, int iters, double* rate, double* ms_out)
     CU(cudaEventElapsedTime(&ms, c->ev[EV_START], c->ev[EV_END]));
     *rate = unit_peak_work(unit, iters, grid) / ((double)ms * 1e-3);
     if (ms_out) *ms_out = ms;
+    return MCE_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Device group: one box, one process, one host thread per GPU.
+// NCCL is bound at run time (dlopen of libnccl.so.2: the library links against nothing but the CUDA runtime, and a
+// Python process keeps whatever NCCL torch brought); without it every device uploads the host arrays itself.
+namespace {
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load() {
+        if (handle) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            handle = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+            if (handle) break;
+        }
+        if (!handle) return false;
+        CommInitAll = reinterpret_cast<decltype(CommInitAll)>(dlsym(handle, "ncclCommInitAll"));
+        CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(handle, "ncclCommDestroy"));
+        Broadcast = reinterpret_cast<decltype(Broadcast)>(dlsym(handle, "ncclBroadcast"));
+        GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(handle, "ncclGetErrorString"));
+        if (!CommInitAll || !CommDestroy || !Broadcast || !GetErrorString) {
+            dlclose(handle);
+            handle = nullptr;
+            return false;
+        }
+        return true;
+    }
+};
+
+}  // namespace
+
+struct mce_group {
+    std::vector<mce_ctx*> ctx;          // one per device, rank order
+    std::vector<ncclComm_t> comm;       // empty without NCCL
+    std::vector<DevBuf> raw_q, raw_r, logl, w;   // per rank: broadcast samples, this rank's slices of logL and weights
+    NcclApi nccl;
+    std::mutex mu;
+};
+
+namespace {
+
+void shard_rows(long long n, int rank, int world, long long* lo, long long* hi) {
+    const long long base = n / world, rem = n % world;
+    *lo = rank * base + (rank < rem ? rank : rem);
+    *hi = *lo + base + (rank < rem ? 1 : 0);
+}
+
+// One rank of mce_group_evidence: rows [lo, hi) of the query set against the whole reference set -> partial triples.
+int group_rank_evidence(mce_group* g, int r, const mce_problem& p, long long lo, long long hi, double* partials,
+                        mce_result* sub) {
+    mce_ctx* c = g->ctx[r];
+    const int world = (int)g->ctx.size();
+    CU(cudaSetDevice(c->device));
+    mce_problem q = p;
+    q.q_begin = lo;
+    q.q_end = hi;
+    q.flags |= MCE_FLAG_PARTIALS;
+    memset(sub, 0, sizeof(*sub));
+    sub->partials = partials;
+    const bool bcast = !g->comm.empty() && world > 1 && !p.query_rows && !p.ref_rows;
+    if (bcast) {
+        // the sample arrays go to rank 0 once and from there over NVLink to everybody (ncclBroadcast on every rank's
+        // own stream, which also orders it before the kernels); logL and the weights are needed for this rank's rows only
+        cudaStream_t st = c->stream;
+        const size_t esz = (p.flags & MCE_FLAG_F32_SAMPLES) ? sizeof(float) : sizeof(double);
+        auto share = [&](DevBuf& buf, const void* host, long long n, long long ld) -> int {
+            const size_t bytes = ((size_t)(n - 1) * ld + p.d) * esz;
+            int rc = buf.ensure(bytes);
+            if (rc) return rc;
+            if (r == 0) CU(cudaMemcpyAsync(buf.p, host, bytes, cudaMemcpyHostToDevice, st));
+            const ncclResult_t nr = g->nccl.Broadcast(buf.p, buf.p, bytes, ncclChar, 0, g->comm[r], st);
+            if (nr != ncclSuccess) return fail(MCE_ERR_CUDA, "ncclBroadcast failed on rank %d: %s", r, g->nccl.GetErrorString(nr));
+            return MCE_OK;
+        };
+        int rc = share(g->raw_q[r], p.query, p.n_query, p.ld_query);
+        if (rc) return rc;
+        q.query = g->raw_q[r].p;
+        if (p.ref) {
+            rc = share(g->raw_r[r], p.ref, p.n_ref, p.ld_ref);
+            if (rc) return rc;
+            q.ref = g->raw_r[r].p;
+        }
+        const size_t nb = (size_t)(hi - lo) * 8;
+        rc = g->logl[r].ensure(nb);
+        if (rc) return rc;
+        rc = g->w[r].ensure(nb);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(g->logl[r].p, p.logl + lo, nb, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(g->w[r].p, p.weights + lo, nb, cudaMemcpyHostToDevice, st));
+        q.logl = g->logl[r].as<double>() - lo;      // indexed by global row
+        q.weights = g->w[r].as<double>() - lo;
+        q.flags |= MCE_FLAG_DEVICE_PTRS;
+    }
+    return mce_evidence(c, &q, sub);
+}
+
+}  // namespace
+
+extern "C" {
+
+int mce_group_create(int n_devices, const int* device_ids, mce_group** out) {
+    if (!out) return fail(MCE_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    const int have = mce_device_count();
+    if (have == 0) return fail(MCE_ERR_CUDA, "no CUDA device available; mcevidence_b200 has no CPU fallback");
+    if (n_devices <= 0) n_devices = have;
+    if (n_devices > have) return fail(MCE_ERR_ARG, "%d devices requested, %d present", n_devices, have);
+    mce_group* g = new (std::nothrow) mce_group();
+    if (!g) return fail(MCE_ERR_NOMEM, "out of host memory");
+    std::vector<int> ids(n_devices);
+    for (int i = 0; i < n_devices; ++i) ids[i] = device_ids ? device_ids[i] : i;
+    for (int i = 0; i < n_devices; ++i) {
+        mce_ctx* c = nullptr;
+        const int rc = mce_ctx_create(ids[i], &c);
+        if (rc) {
+            mce_group_destroy(g);
+            return rc;
+        }
+        g->ctx.push_back(c);
+    }
+    g->raw_q.resize(n_devices);
+    g->raw_r.resize(n_devices);
+    g->logl.resize(n_devices);
+    g->w.resize(n_devices);
+    const char* no_nccl = getenv("MCE_GROUP_NO_NCCL");
+    if (n_devices > 1 && !(no_nccl && no_nccl[0] == '1') && g->nccl.load()) {
+        g->comm.resize(n_devices);
+        const ncclResult_t nr = g->nccl.CommInitAll(g->comm.data(), n_devices, ids.data());
+        if (nr != ncclSuccess) {
+            g->comm.clear();     // fall back to one upload per device
+            cudaGetLastError();
+        }
+    }
+    *out = g;
+    return MCE_OK;
+}
+
+void mce_group_destroy(mce_group* g) {
+    if (!g) return;
+    for (size_t r = 0; r < g->ctx.size(); ++r) {
+        cudaSetDevice(g->ctx[r]->device);
+        if (r < g->comm.size()) g->nccl.CommDestroy(g->comm[r]);
+        if (r < g->raw_q.size()) {
+            g->raw_q[r].release();
+            g->raw_r[r].release();
+            g->logl[r].release();
+            g->w[r].release();
+        }
+        mce_ctx_destroy(g->ctx[r]);
+    }
+    delete g;
+}
+
+int mce_group_size(const mce_group* g) { return g ? (int)g->ctx.size() : 0; }
+int mce_group_uses_nccl(const mce_group* g) { return g && !g->comm.empty() ? 1 : 0; }
+
+int mce_group_set_option(mce_group* g, const char* name, int value) {
+    if (!g) return fail(MCE_ERR_ARG, "group is NULL");
+    for (mce_ctx* c : g->ctx) {
+        const int rc = mce_ctx_set_option(c, name, value);
+        if (rc) return rc;
+    }
+    return MCE_OK;
+}
+
+int mce_group_evidence(mce_group* g, const mce_problem* problem, mce_result* result) {
+    if (!g || !problem || !result) return fail(MCE_ERR_ARG, "group, problem or result is NULL");
+    if (!result->logE) return fail(MCE_ERR_ARG, "result.logE is NULL");
+    if (problem->flags & MCE_FLAG_DEVICE_PTRS) return fail(MCE_ERR_ARG, "a device group takes host arrays");
+    if (problem->q_begin != 0 || problem->q_end != 0) return fail(MCE_ERR_ARG, "a device group shards the rows itself: no query row range");
+    if (result->dknn || result->idx) return fail(MCE_ERR_ARG, "neighbour arrays are not gathered by a device group");
+    int rc = validate(problem, true);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g->mu);
+    const int world = (int)g->ctx.size();
+    const int kmax = problem->kmax < 2 ? 2 : problem->kmax;
+    const int nk = kmax - 1;
+    std::vector<double> parts((size_t)world * nk * 3);
+    std::vector<mce_result> subs(world);
+    std::vector<int> rcs(world, MCE_OK);
+    std::vector<std::string> errs(world);
+    std::vector<std::thread> threads;
+    for (int r = 0; r < world; ++r) {
+        threads.emplace_back([&, r]() {
+            long long lo, hi;
+            shard_rows(problem->n_query, r, world, &lo, &hi);
+            if (hi <= lo) {          // more devices than rows: an empty shard contributes nothing
+                for (int k = 0; k < nk; ++k) {
+                    parts[((size_t)r * nk + k) * 3] = -INFINITY;
+                    parts[((size_t)r * nk + k) * 3 + 1] = 0.0;
+                    parts[((size_t)r * nk + k) * 3 + 2] = 0.0;
+                }
+                memset(&subs[r], 0, sizeof(mce_result));
+                return;
+            }
+            rcs[r] = group_rank_evidence(g, r, *problem, lo, hi, parts.data() + (size_t)r * nk * 3, &subs[r]);
+            if (rcs[r]) errs[r] = g_err;     // the message is thread-local
+        });
+    }
+    for (auto& t : threads) t.join();
+    for (int r = 0; r < world; ++r)
+        if (rcs[r]) return fail(rcs[r], "device %d: %s", g->ctx[r]->device, errs[r].c_str());
+    // the exchange after the search is 3 (kmax - 1) doubles per device, already on the host of this one process
+    std::vector<double> total((size_t)nk * 3);
+    rc = mce_combine_partials(world, nk, parts.data(), total.data());
+    if (rc) return rc;
+    result->log_jacobian = subs[0].log_jacobian;
+    result->stats = subs[0].stats;
+    for (int r = 1; r < world; ++r) {     // the slowest device sets the time; counts add up
+        if (subs[r].stats.ms_total > result->stats.ms_total) result->stats.ms_total = subs[r].stats.ms_total;
+        result->stats.pairs += subs[r].stats.pairs;
+        result->stats.rows_rescanned += subs[r].stats.rows_rescanned;
+        result->stats.launches += subs[r].stats.launches;
+    }
+    if ((problem->flags & MCE_FLAG_PARTIALS) && result->partials) memcpy(result->partials, total.data(), total.size() * 8);
+    return mce_finalize(total.data(), nk, problem->d, problem->ref ? 1 : 0, problem->n_query, problem->log_sum_w,
+                        result->log_jacobian, problem->log_prior_volume, result->logE, result->var_logE);
+}
+
+int mce_group_evidence_batch(mce_group* g, int n, const mce_problem* problems, mce_result* results) {
+    if (!g) return fail(MCE_ERR_ARG, "group is NULL");
+    if (n < 0 || (n > 0 && (!problems || !results))) return fail(MCE_ERR_ARG, "bad batch arguments");
+    std::lock_guard<std::mutex> lk(g->mu);
+    const int world = (int)g->ctx.size();
+    // chain-per-GPU: largest first to the least loaded device (planck_mcevidence.py:149-156 splits per data set)
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    auto cost = [&](int i) { return (double)problems[i].n_query * (double)(problems[i].ref ? problems[i].n_ref : problems[i].n_query); };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost(a) > cost(b); });
+    std::vector<std::vector<int>> mine(world);
+    std::vector<double> load(world, 0.0);
+    for (int i : order) {
+        const int r = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        mine[r].push_back(i);
+        load[r] += cost(i);
+    }
+    std::vector<int> rcs(world, MCE_OK);
+    std::vector<std::string> errs(world);
+    std::vector<std::thread> threads;
+    for (int r = 0; r < world; ++r) {
+        threads.emplace_back([&, r]() {
+            const int m = (int)mine[r].size();
+            if (m == 0) return;
+            std::vector<mce_problem> ps(m);
+            std::vector<mce_result> rs(m);
+            for (int j = 0; j < m; ++j) {
+                ps[j] = problems[mine[r][j]];
+                rs[j] = results[mine[r][j]];
+            }
+            rcs[r] = mce_evidence_batch(g->ctx[r], m, ps.data(), rs.data());
+            if (rcs[r]) errs[r] = g_err;
+            for (int j = 0; j < m; ++j) results[mine[r][j]] = rs[j];
+        });
+    }
+    for (auto& t : threads) t.join();
+    for (int r = 0; r < world; ++r)
+        if (rcs[r]) return fail(rcs[r], "device %d: %s", g->ctx[r]->device, errs[r].c_str());
     return MCE_OK;
 }
 

@@ -204,21 +204,25 @@ __device__ __forceinline__ void tc_push(const TcQueue& q, uint32_t query, uint32
     const unsigned long long item = ((unsigned long long)query << 32) | (unsigned long long)ridx;
     const uint32_t addr = q.items + (pos & (TC_QCAP - 1)) * 8u;
     long long t0 = 0;
-    for (bool first = true;; first = false) {
+    for (unsigned int it = 1u;; ++it) {
         if (pos - lds_u32_volatile(q.ctrl + 4) < TC_QCAP) {
             sts_u64_volatile(addr, item);
             break;
         }
-        if (first) t0 = clock64();
         __nanosleep(64);
-        if (*reinterpret_cast<volatile unsigned int*>(&g_tc_stuck[0]) != 0u) break;
-        if (clock64() - t0 > 1000000000LL) {
-            if (atomicCAS(&g_tc_stuck[0], 0u, 2u) == 0u) {
-                g_tc_stuck[1] = pos;
-                g_tc_stuck[2] = lds_u32_volatile(q.ctrl + 4);
-                g_tc_stuck[3] = blockIdx.x;
+        if ((it & 255u) == 0u) {   // the give-up bookkeeping costs an L2 round trip: not on every poll
+            if (*reinterpret_cast<volatile unsigned int*>(&g_tc_stuck[0]) != 0u) break;
+            const long long now = clock64();
+            if (t0 == 0) {
+                t0 = now;
+            } else if (now - t0 > 1000000000LL) {
+                if (atomicCAS(&g_tc_stuck[0], 0u, 2u) == 0u) {
+                    g_tc_stuck[1] = pos;
+                    g_tc_stuck[2] = lds_u32_volatile(q.ctrl + 4);
+                    g_tc_stuck[3] = blockIdx.x;
+                }
+                break;
             }
-            break;
         }
     }
 }
@@ -303,7 +307,8 @@ __device__ __forceinline__ void tc_boot_insert(float (&t)[TC_BOOT], float x) {
 // MMA warps 0 tile landed, 1 accumulator free, 2 MMAs + commit issued; epilogue warp 0 (query block 0, columns 0-63)
 // 5 accumulator full, 6 accumulator released, 7 tile done; epilogue warp 4 (block 1) 8, 9, 10; producer 11 slot free
 // MODE: 0 production, 1 validation (every pair also evaluated exactly, first tile dumped), 2 timeline, 3 / 4 timing
-// experiments whose results are garbage (3: the epilogue skips the TMEM loads, 4: loads without the threshold test)
+// experiments whose results are garbage (3: the epilogue skips the TMEM loads, 4: loads without the threshold test,
+// 5: loads and threshold test but no column ever passes -- the cost of the scan without any hit)
 #define TC_MARK(IT, SLOT)                                                                            \
     do {                                                                                             \
         if constexpr (MODE == 2) {                                                                          \
@@ -494,15 +499,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
         const uint32_t ctrl = queue.ctrl;
         const float* img = p.tiles;
         const int d = p.d;
-        uint32_t head = 0;
+        uint32_t head = 0, idle = 0;
         for (;;) {
             const uint32_t done = lds_u32_volatile(ctrl + 8);
             const uint32_t tail = lds_u32_volatile(ctrl);
             const uint32_t avail = tail - head;
             if (avail == 0) {
                 if (done == (uint32_t)TC_EPI_WARPS) break;
-                if (*reinterpret_cast<volatile unsigned int*>(&g_tc_stuck[0]) != 0u) break;
-                __nanosleep(128);
+                if ((++idle & 255u) == 0u && *reinterpret_cast<volatile unsigned int*>(&g_tc_stuck[0]) != 0u) break;
+                __nanosleep(64);
                 continue;
             }
             // pop the written prefix of the next 32 positions: a reserved slot may not have been written yet, and its
@@ -514,7 +519,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
             const uint32_t unwritten = __ballot_sync(0xffffffffu, item == TC_QEMPTY);
             const uint32_t n = unwritten ? (uint32_t)(__ffs((int)unwritten) - 1) : 32u;
             if (n == 0u) {
-                if (*reinterpret_cast<volatile unsigned int*>(&g_tc_stuck[0]) != 0u) break;
+                if ((++idle & 255u) == 0u && *reinterpret_cast<volatile unsigned int*>(&g_tc_stuck[0]) != 0u) break;
                 __nanosleep(32);
                 continue;
             }
@@ -559,7 +564,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
         const uint32_t slot_bar0 = smem_u32(&bar_free[0]), slot_bar_end = slot_bar0 + (uint32_t)NS * 8u;
         const uint32_t ring0 = smem_u32(ring);
         // invalid queries never pass: th - e_q is NaN (th starts at -inf) or +inf
-        const float e_q = st.valid ? st.e_q : -CUDART_INF_F;
+        const float e_q = (st.valid && MODE != 5) ? st.e_q : -CUDART_INF_F;   // MODE 5: nothing ever passes
 
         if (MODE <= 2 && nt > 0 && L + 1 <= TC_BOOT) {
             // Bootstrap: the (L+1)-th largest coarse score c among this thread's columns of the unit's first tile.
@@ -608,7 +613,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
             tc_fence_after();
             if (quad == 0 && half == 0) TC_MARK(it, 5 + 3 * mb);
             const uint32_t taddr = tlane + 256u * buf;
-            if constexpr (MODE <= 2) {
+            if constexpr (MODE <= 2 || MODE == 5) {
                 const float tcut = lds_f32_volatile(st.th_addr) - e_q;
                 uint32_t v[TC_HALF_COLS];
                 tmem_ld64_wait(taddr, v);
@@ -702,6 +707,7 @@ int tc_launch_k(const TcFilterParams& tp, unsigned grid, size_t smem, cudaStream
         if (tp.timeline) return tc_launch_mode<KSTEPS, 2>(tp, grid, smem, st);
         if (tp.perf_mode == 1) return tc_launch_mode<KSTEPS, 3>(tp, grid, smem, st);
         if (tp.perf_mode == 2) return tc_launch_mode<KSTEPS, 4>(tp, grid, smem, st);
+        if (tp.perf_mode == 3) return tc_launch_mode<KSTEPS, 5>(tp, grid, smem, st);
     }
     if (tp.check) return tc_launch_mode<KSTEPS, 1>(tp, grid, smem, st);
     return tc_launch_mode<KSTEPS, 0>(tp, grid, smem, st);

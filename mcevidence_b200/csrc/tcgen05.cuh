@@ -130,17 +130,25 @@ __device__ __forceinline__ bool tc_try_wait(uint32_t bar, uint32_t parity) {
 // returns at once, so the kernel unwinds (its results are garbage) and the host reports the record.
 static __device__ unsigned int g_tc_stuck[4];   // [0] flag, [1] barrier address, [2] parity | warp << 8, [3] blockIdx.x
 __device__ __forceinline__ void tc_wait_slow(uint32_t bar, uint32_t parity, uint32_t pause_ns) {
-    const long long t0 = clock64();
-    while (!tc_try_wait(bar, parity)) {
+    // The give-up bookkeeping (a global-memory flag and the clock) is looked at once per 1024 polls only: a load of
+    // the flag costs an L2 round trip, and with it inside every poll each hand-over would wake up that much later.
+    long long t0 = 0;
+    for (unsigned int it = 1u;; ++it) {
+        if (tc_try_wait(bar, parity)) return;
         if (pause_ns) __nanosleep(pause_ns);
-        if (*reinterpret_cast<volatile unsigned int*>(&g_tc_stuck[0]) != 0u) return;
-        if (clock64() - t0 > 1000000000LL) {
-            if (atomicCAS(&g_tc_stuck[0], 0u, 1u) == 0u) {
-                g_tc_stuck[1] = bar;
-                g_tc_stuck[2] = parity | ((threadIdx.x >> 5) << 8);
-                g_tc_stuck[3] = blockIdx.x;
+        if ((it & 1023u) == 0u) {
+            if (*reinterpret_cast<volatile unsigned int*>(&g_tc_stuck[0]) != 0u) return;
+            const long long now = clock64();
+            if (t0 == 0) {
+                t0 = now;
+            } else if (now - t0 > 1000000000LL) {
+                if (atomicCAS(&g_tc_stuck[0], 0u, 1u) == 0u) {
+                    g_tc_stuck[1] = bar;
+                    g_tc_stuck[2] = parity | ((threadIdx.x >> 5) << 8);
+                    g_tc_stuck[3] = blockIdx.x;
+                }
+                return;
             }
-            return;
         }
     }
 }

@@ -93,6 +93,16 @@ class MCEvidence(object):
         if ndim is None:
             ndim = self.gd.nparamMC
         self.ndim = ndim
+        # Limits of the CUDA library that scikit-learn does not have (include/mcevidence_b200.h): checked here, before
+        # anything is sent to the GPU, so that the error names the argument instead of coming back from the device.
+        if self.ndim > _lib.MCE_MAX_DIM:
+            raise ValueError('ndim=%d: the B200 filter kernels serve at most %d parameters (MCE_MAX_DIM); select fewer '
+                             'columns with ndim= / --ndim' % (self.ndim, _lib.MCE_MAX_DIM))
+        kcap = _lib.MCE_MAX_NEIGHBOURS + (0 if self.split else 1)
+        if self.kmax > kcap:
+            raise ValueError('kmax=%d: at most %d true neighbours per sample are searched (MCE_MAX_NEIGHBOURS), i.e. '
+                             'kmax <= %d in %s mode' % (self.kmax, _lib.MCE_MAX_NEIGHBOURS, kcap,
+                                                        'cross' if self.split else 'auto'))
         self.info['NparamsCosmo'] = self.ndim
         self.info['Nsamples'] = ', '.join([str(x) for x in self.nsample])
         self.logger.info('chain array dimensions: %s x %s =' % (self.nsample, self.ndim))

@@ -13,9 +13,11 @@ under ``torchrun`` (or a single process / single GPU) -- and every evidence runs
     python -m torch.distributed.run --nproc-per-node 8 planck_mcevidence.py --rootdir ... -nc 4
 
 Layout expected: ``<rootdir>/<model>/<data_dir>/<model>_<data>_<i>.txt`` with ``<model>_<data>.ranges``
-next to the chains.  New flags: ``--rootdir`` (the reference hard-codes it, ``:173``), ``--h0prior`` to
-apply the H0 = 73.24 +- 1.74 importance weight of the reference (``:56-58``; there it needs a getdist
-object, here the ``H0*`` column is located through ``<root>.paramnames``).
+next to the chains.  New flags: ``--rootdir`` (the reference hard-codes it, ``:173``).  As in the reference
+(``:344``) every evidence carries the H0 = 73.24 +- 1.74 importance weight (``:56-58``; there it needs a getdist
+object, here the ``H0*`` column is located through ``<root>.paramnames``): by default it is applied to every root that
+has a ``.paramnames`` file, ``--h0prior`` makes a missing file an error and ``--no-h0prior`` switches the weight off (the
+default output directory then drops the reference's ``_H0Reiss2016`` suffix).
 """
 from __future__ import absolute_import, print_function
 
@@ -67,12 +69,16 @@ def build_parser():
                    help='Burn-in fraction')
     p.add_argument('-t', '--thin', '--thinfrac', dest='thinfrac', default=0, type=float, help='Thinning fraction')
     p.add_argument('-o', '--out', '--outdir', dest='outdir', default='planck_mce_fullGrid_R2_H0Reiss2016',
-                   help='Output directory name')
+                   help='Output directory name (default: planck_mce_fullGrid_R2_H0Reiss2016, as in the reference, or '
+                        'planck_mce_fullGrid_R2 with --no-h0prior)')
     p.add_argument('--N', '--name', dest='name', default='mce', help='base name for output files')
     p.add_argument('-v', '--verbose', dest='verbose', default=1, type=int, help='increase output verbosity')
     p.add_argument('--rootdir', default='COM_CosmoParams_fullGrid_R2.00', help='root of the CosmoMC chain grid')
     p.add_argument('--datasets', nargs='*', default=None, help='data-set names (default: the Planck 2015 list)')
-    p.add_argument('--h0prior', action='store_true', help='importance-weight with H0 = 73.24 +- 1.74 (needs .paramnames)')
+    p.add_argument('--h0prior', dest='h0prior', action='store_const', const='on', default='auto',
+                   help='importance-weight with H0 = 73.24 +- 1.74 as the reference always does (planck_mcevidence.py:344); '
+                        'needs <root>.paramnames.  Default: applied to every root that has a .paramnames file with H0')
+    p.add_argument('--no-h0prior', dest='h0prior', action='store_const', const='off', help='un-weighted evidences')
     return p
 
 
@@ -87,16 +93,31 @@ def avail_model_list(rootdir, dd, nmax=0, sorter=MODELS):
     return [r for r, _ in pairs], [m for _, m in pairs]
 
 
-def h0_column(root):
-    """Index (within the parameter columns) of ``H0*`` according to ``<root>.paramnames``."""
+def h0_column(root, required=True):
+    """Index (within the parameter columns) of ``H0*`` according to ``<root>.paramnames`` (None when the file is
+    missing and the weight was not asked for explicitly)."""
     fn = root + '.paramnames'
     if not os.path.exists(fn):
+        if not required:
+            return None
         raise IOError('--h0prior needs %s' % fn)
     names = [line.split()[0] for line in open(fn) if line.strip()]
     for i, nm in enumerate(names):
         if nm.rstrip('*') == 'H0':
             return i
+    if not required:
+        return None
     raise ValueError('no H0 parameter in %s' % fn)
+
+
+def h0_gauss_lnp(col):
+    """-log of the H0 = 73.24 +- 1.74 importance weight (Riess et al. 2016; planck_mcevidence.py:56-58) on sample column
+    ``col``; the column index comes from .paramnames and is checked against the samples."""
+    def func(s):
+        if col >= s.shape[1]:
+            raise ValueError('H0 is parameter %d of .paramnames but the chain has only %d parameter columns' % (col, s.shape[1]))
+        return 0.5 * ((s[:, col] - 73.24) / 1.74) ** 2
+    return func
 
 
 def analyse_dataset(args, dd, chain_exts, mce_cols):
@@ -117,9 +138,12 @@ def analyse_dataset(args, dd, chain_exts, mce_cols):
             vol_norm = par['volume']                  # prior volumes are relative to the base model
         prior_volume = par['volume'] / vol_norm
         isfunc = None
-        if args.h0prior:
-            col = h0_column(fname)
-            isfunc = lambda s, c=col: 0.5 * ((s[:, c] - 73.24) / 1.74) ** 2      # noqa: E731
+        if args.h0prior != 'off':
+            col = h0_column(fname, required=args.h0prior == 'on')
+            if col is None:
+                print('*** no H0 column known for %s (no .paramnames): evidence NOT H0-weighted' % fname)
+            else:
+                isfunc = h0_gauss_lnp(col)
         nc_read, nc_use = '', ''
         for icc, cext in enumerate(chain_exts):
             e, info = MCEvidence(fname + cext, ndim=par['ndim'], isfunc=isfunc, priorvolume=prior_volume,
@@ -151,6 +175,8 @@ def main(argv=None):
     from tabulate import tabulate
     args = build_parser().parse_args(argv)
     assert args.kmax >= 2, 'kmax must be >=2'
+    if args.h0prior == 'off' and args.outdir == 'planck_mce_fullGrid_R2_H0Reiss2016':
+        args.outdir = 'planck_mce_fullGrid_R2'      # the reference's directory name promises the H0 weight
     logging.basicConfig(level=[logging.WARNING, logging.INFO][min(args.verbose, 1)] if args.verbose < 2 else logging.DEBUG)
 
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))

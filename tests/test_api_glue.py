@@ -62,3 +62,18 @@ def test_covtype_single_and_batches(oracle_ctx):
         assert np.abs(res[i] - want).max() < 1e-9
     with pytest.raises(ValueError):
         M.MCEvidence([c], verbose=0).evidence(covtype='bogus')
+
+
+def test_library_limits_raise_before_the_gpu():
+    """ndim > MCE_MAX_DIM and more than MCE_MAX_NEIGHBOURS neighbours are rejected in the constructor."""
+    import MCEvidence as M
+    rng = np.random.default_rng(0)
+    wide = np.column_stack((np.ones(200), np.zeros(200), rng.normal(size=(200, 70))))
+    with pytest.raises(ValueError, match='MCE_MAX_DIM'):
+        M.MCEvidence([wide], kmax=2, verbose=0)
+    M.MCEvidence([wide], kmax=2, ndim=64, verbose=0)
+    with pytest.raises(ValueError, match='MCE_MAX_NEIGHBOURS'):
+        M.MCEvidence([wide], kmax=18, ndim=5, verbose=0)
+    M.MCEvidence([wide], kmax=17, ndim=5, verbose=0)
+    with pytest.raises(ValueError, match='MCE_MAX_NEIGHBOURS'):
+        M.MCEvidence([wide], kmax=17, ndim=5, split=True, verbose=0)

@@ -115,7 +115,7 @@ def test_planck_grid_driver(tmp_path):
     rootdir, out = str(tmp_path / 'grid'), str(tmp_path / 'out')
     grid = write_cosmomc_grid(rootdir, nchains=2, nrows=700)
     dsets = ['plikHM_TT_lowTEB', 'plikHM_TT_lowTEB_post_BAO']
-    P.main(['--rootdir', rootdir, '-o', out, '-k', '2', '-b', '0.3', '-v', '0', '--datasets'] + dsets)
+    P.main(['--rootdir', rootdir, '-o', out, '-k', '2', '-b', '0.3', '-v', '0', '--no-h0prior', '--datasets'] + dsets)
     vol_base = {dd: grid[(dd, 'base')][2] for dd in dsets}
     for dd in dsets:
         df = pd.read_csv(os.path.join(out, 'AllChains', 'csv', 'mce_%s.csv' % dd), index_col=0)
