@@ -142,6 +142,7 @@ struct mce_ctx {
     std::vector<mce_ctx*> lanes;
     std::vector<cudaEvent_t> ev_pool;   // start / end events of the problems of a batch
     int opt_lanes = 8;
+    int opt_sweep_seed = 1;         // sweep: one filter launch per chunk, seeded with the previous chunk's thresholds
     int share = 1;                  // the work-split model assumes sm_count / share SMs (several problems in flight)
 };
 
@@ -655,6 +656,16 @@ int enqueue_problem(mce_ctx* c, const Run& r, Pending& pd) {
         fp.list_len = list_len;
         fp.d = d;
         fp.chunk_tile0 = d_chunk_tile0;
+        fp.chunk_base = 0;
+        fp.seed_th = 0;
+        // Sweep: one launch per reference chunk, in order, each covering every query block; chunk c starts from the final
+        // thresholds of chunk c - 1 (a valid floor because the batches are nested prefixes), so the pass makes about as
+        // many list insertions as one unchunked scan instead of restarting the lists at every batch size.
+        const int nlaunch = (sweep_auto && c->opt_sweep_seed) ? chunks : 1;
+        if (nlaunch > 1) {
+            fp.ref_chunks = 1;
+            fp.seed_th = 1;
+        }
         if (use_tc) {
             // Bound on |coarse - exact| per pair, e = slack_qr |q| Rmax + slack_rr Rmax^2: both operands are
             // truncated to TF32 (2^-10 relative each, 2^-9 (1 + 2^-10) on a product, summed with Cauchy-Schwarz),
@@ -690,10 +701,17 @@ int enqueue_problem(mce_ctx* c, const Run& r, Pending& pd) {
             tp.check = c->opt_tc_check;
             tp.perf_mode = c->opt_tc_perf;
             tp.mma_warps = c->opt_tc_mma_warps;
-            if (launch_tc_filter(tp, st, &launches) != 0)
-                return fail(MCE_ERR_CUDA, "tensor-core filter launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        } else if (launch_filter(fp, cfg, st, &launches) != 0) {
-            return fail(MCE_ERR_CUDA, "filter launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            for (int cb = 0; cb < nlaunch; ++cb) {
+                tp.f.chunk_base = cb;
+                if (launch_tc_filter(tp, st, &launches) != 0)
+                    return fail(MCE_ERR_CUDA, "tensor-core filter launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            }
+        } else {
+            for (int cb = 0; cb < nlaunch; ++cb) {
+                fp.chunk_base = cb;
+                if (launch_filter(fp, cfg, st, &launches) != 0)
+                    return fail(MCE_ERR_CUDA, "filter launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            }
         }
     }
     CU(cudaEventRecord(c->ev[EV_FILTER], st));
@@ -1043,6 +1061,7 @@ int mce_ctx_set_option(mce_ctx* c, const char* name, int value) {
         c->opt_sync = value;
     }
     else if (!strcmp(name, "tail_chunks")) c->opt_tail = value;
+    else if (!strcmp(name, "sweep_seed")) c->opt_sweep_seed = value != 0;
     else if (!strcmp(name, "batch_lanes")) {
         if (value < 1 || value > 32) return fail(MCE_ERR_ARG, "batch_lanes must be in [1, 32]");
         c->opt_lanes = value;

@@ -86,6 +86,11 @@ struct FilterParams {
     int d;
     const int* chunk_tile0;  // batch-size sweep: ref_chunks + 1 tile indices, chunk r = tiles [chunk_tile0[r], chunk_tile0[r+1])
                              // (the prefix boundaries of MCEvidence.py:1039-1045); nullptr: uniform tiles_per_chunk
+    int chunk_base;          // sweep: this launch covers reference chunk chunk_base + (unit's chunk) only -- one launch per
+                             // chunk, in order, so that chunk c can start from the final thresholds of chunk c - 1
+    int seed_th;             // sweep: 1 = a unit of chunk c >= 1 starts from the threshold plane of chunk c - 1 as a floor.
+                             // Valid because batches are nested prefixes: whoever reads chunk c also reads chunks < c, and
+                             // L references with a score >= that floor are already in their lists.
 };
 // first and one-past-last tile of reference chunk r of a split query block
 __device__ __forceinline__ void chunk_tile_range(const FilterParams& p, int r, int* t0, int* t1) {

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
     } else {
         const int v = blockIdx.x - p.nfull;
         const int rem = p.nqblocks - p.nfull;
-        rchunk = v / rem;
+        rchunk = v / rem + p.chunk_base;
         qblock = p.nfull + v % rem;
         chunk_tile_range(p, rchunk, &t0, &t1);
     }
@@ -145,6 +145,8 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
 #pragma unroll
         for (int c = 0; c < D; ++c) q[t][c] = valid ? (float)src[c] : 0.f;
         th[t] = valid ? -CUDART_INF_F : CUDART_INF_F;
+        if (valid && p.seed_th && rchunk > 0)   // sweep: floor = final threshold of the previous chunk
+            th[t] = p.cand_th[cand_th_offset(rchunk - 1, ql, p.nq_pad, p.ntail_pad, p.tail_q0)];
         for (int e = 0; e < L; ++e) {
             ls[(t * L + e) * NT + tid] = -CUDART_INF_F;
             li[(t * L + e) * NT + tid] = -1;
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
                             if (s > th[t]) {
                                 const int ridx = jbase + j0 + e;
                                 if (ridx != self0 + t * NT)
-                                    th[t] = list_insert(ls + t * L * NT + tid, li + t * L * NT + tid, L, s, ridx);
+                                    th[t] = fmaxf(th[t], list_insert(ls + t * L * NT + tid, li + t * L * NT + tid, L, s, ridx));
                             }
                         }
                     }
@@ -360,7 +362,7 @@ __global__ void __launch_bounds__(FILTER_THREADS) knn_filter_kernel(const Filter
                             if (acc[t][e] > th[t]) {
                                 const int ridx = jbase + j0 + e;
                                 if (ridx != self0 + t * NT)
-                                    th[t] = list_insert(ls + t * L * NT + tid, li + t * L * NT + tid, L, acc[t][e], ridx);
+                                    th[t] = fmaxf(th[t], list_insert(ls + t * L * NT + tid, li + t * L * NT + tid, L, acc[t][e], ridx));
                             }
                         }
                     }

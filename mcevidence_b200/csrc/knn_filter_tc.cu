@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
     } else {
         const int v = blockIdx.x - p.nfull;
         const int rem = p.nqblocks - p.nfull;
-        rchunk = v / rem;
+        rchunk = v / rem + p.chunk_base;
         qblock = p.nfull + v % rem;
         chunk_tile_range(p, rchunk, &t0, &t1);
     }
@@ -418,7 +418,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
         st.valid = valid;
         st.d = p.d;
         if (half == 0) {
-            th_s[qslot] = -CUDART_INF_F;
+            // sweep: the final threshold of the previous chunk is a floor for this one (see FilterParams::seed_th)
+            th_s[qslot] = (valid && p.seed_th && rchunk > 0)
+                              ? p.cand_th[cand_th_offset(rchunk - 1, ql, p.nq_pad, p.ntail_pad, p.tail_q0)]
+                              : -CUDART_INF_F;
             for (int e = 0; e < L; ++e) {
                 ls[e * TC_QUERIES + qslot] = -CUDART_INF_F;
                 li[e * TC_QUERIES + qslot] = -1;

@@ -165,6 +165,10 @@ def test_batch_size_sweep_is_bit_identical(engine, cross):
     kw = dict(ndim=d, W=W, mu=mu, log_jacobian=logj, log_sum_w=math.log(w.sum()), log_prior_volume=0.3)
     got = ctx.evidence_sweep(s, logl, w, kmax, rows, ref=ref, **kw)
     assert got[0]['stats']['filter_mode'] == (16 if engine else got[0]['stats']['filter_mode'])
+    ctx.set_option('sweep_seed', 0)          # one launch, lists restarted per range: the same numbers
+    for g, g0 in zip(got, ctx.evidence_sweep(s, logl, w, kmax, rows, ref=ref, **kw)):
+        np.testing.assert_array_equal(g['logE'], g0['logE'])
+    ctx.set_option('sweep_seed', 1)
     for nb, g in zip(rows, got):
         want = ctx.evidence(s[:nb], logl[:nb], w[:nb], kmax, ref=ref, **kw)
         np.testing.assert_array_equal(g['logE'], want['logE'])
