@@ -14,6 +14,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <thread>
 #include <new>
@@ -142,6 +143,8 @@ struct mce_ctx {
     std::vector<mce_ctx*> lanes;
     std::vector<cudaEvent_t> ev_pool;   // start / end events of the problems of a batch
     int opt_lanes = 8;
+    int opt_stage = 1;              // batches: pack the host arrays into a pinned arena on packer threads
+    PinBuf hstage;
     int opt_sweep_seed = 1;         // sweep: one filter launch per chunk, seeded with the previous chunk's thresholds
     int share = 1;                  // the work-split model assumes sm_count / share SMs (several problems in flight)
 };
@@ -1034,6 +1037,7 @@ void mce_ctx_destroy(mce_ctx* c) {
     for (DevBuf* b : bufs) b->release();
     c->hres.release();
     c->hmeta.release();
+    c->hstage.release();
     for (int i = 0; i < EV_COUNT; ++i)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->hscal) cudaFreeHost(c->hscal);
@@ -1062,6 +1066,7 @@ int mce_ctx_set_option(mce_ctx* c, const char* name, int value) {
     }
     else if (!strcmp(name, "tail_chunks")) c->opt_tail = value;
     else if (!strcmp(name, "sweep_seed")) c->opt_sweep_seed = value != 0;
+    else if (!strcmp(name, "batch_stage")) c->opt_stage = value != 0;
     else if (!strcmp(name, "batch_lanes")) {
         if (value < 1 || value > 32) return fail(MCE_ERR_ARG, "batch_lanes must be in [1, 32]");
         c->opt_lanes = value;
@@ -1170,12 +1175,83 @@ int mce_evidence_batch(mce_ctx* c, int n, const mce_problem* problems, mce_resul
         lane->opt_tc_mma_warps = c->opt_tc_mma_warps;
         lane->share = nl;
     }
+    // Host staging.  A copy from pageable memory waits for the lane's stream and goes through the driver's own bounce
+    // buffer, which made the host side of a batch as long as its device side.  A few packer threads therefore copy every
+    // problem's arrays -- only the d columns that are used, dense -- into one pinned arena, in enqueue order and ahead
+    // of the enqueuing thread; the uploads are then true asynchronous copies that overlap the kernels of other lanes.
+    std::vector<mce_problem> staged(problems, problems + n);
+    std::vector<size_t> arena_off(n, 0);
+    size_t arena_bytes = 0;
+    const size_t arena_cap = (size_t)2 << 30;
+    bool stage = c->opt_stage != 0;
+    for (int i = 0; i < n && stage; ++i) {
+        const mce_problem& q = problems[i];
+        if ((q.flags & MCE_FLAG_DEVICE_PTRS) || q.query_rows || q.ref_rows || validate(&q, true) != MCE_OK) stage = false;
+        const size_t esz = (q.flags & MCE_FLAG_F32_SAMPLES) ? 4 : 8;
+        arena_off[i] = arena_bytes;
+        arena_bytes += (((size_t)q.n_query * q.d + (q.ref ? (size_t)q.n_ref * q.d : 0)) * esz + (size_t)q.n_query * 16 + 255) & ~(size_t)255;
+        if (arena_bytes > arena_cap) stage = false;
+    }
+    std::vector<std::atomic<int>> ready(stage ? n : 0);
+    std::vector<std::thread> packers;
+    std::atomic<int> next_job{0};
+    if (stage) {
+        rc = c->hstage.ensure(arena_bytes);
+        if (rc) return rc;
+        unsigned char* arena = c->hstage.as<unsigned char>();
+        for (int i = 0; i < n; ++i) ready[i].store(0, std::memory_order_relaxed);
+        auto pack_rows = [](unsigned char* dst, const void* src, long long rows, long long ld, int d, size_t esz) {
+            const unsigned char* s0 = static_cast<const unsigned char*>(src);
+            if (ld == d) {
+                memcpy(dst, s0, (size_t)rows * d * esz);
+            } else {
+                for (long long r = 0; r < rows; ++r) memcpy(dst + (size_t)r * d * esz, s0 + (size_t)r * ld * esz, (size_t)d * esz);
+            }
+        };
+        for (int i = 0; i < n; ++i) {      // where every array of problem i will live
+            mce_problem& q = staged[i];
+            const size_t esz = (q.flags & MCE_FLAG_F32_SAMPLES) ? 4 : 8;
+            unsigned char* base = arena + arena_off[i];
+            unsigned char* p_ref = base + (size_t)q.n_query * q.d * esz;
+            unsigned char* p_logl = p_ref + (q.ref ? (size_t)q.n_ref * q.d * esz : 0);
+            q.query = base;
+            q.ld_query = q.d;
+            if (q.ref) {
+                q.ref = p_ref;
+                q.ld_ref = q.d;
+            }
+            q.logl = reinterpret_cast<const double*>(p_logl);
+            q.weights = reinterpret_cast<const double*>(p_logl + (size_t)q.n_query * 8);
+        }
+        unsigned hw = std::thread::hardware_concurrency();
+        const int nthreads = (int)std::min<unsigned>(hw ? hw : 4u, std::min<unsigned>(8u, (unsigned)n));
+        for (int t = 0; t < nthreads; ++t) {
+            packers.emplace_back([&, pack_rows]() {
+                for (;;) {
+                    const int j = next_job.fetch_add(1);
+                    if (j >= n) return;
+                    const int i = order[j];
+                    const mce_problem& src = problems[i];
+                    const mce_problem& dst = staged[i];
+                    const size_t esz = (src.flags & MCE_FLAG_F32_SAMPLES) ? 4 : 8;
+                    pack_rows(static_cast<unsigned char*>(const_cast<void*>(dst.query)), src.query, src.n_query, src.ld_query, src.d, esz);
+                    if (src.ref)
+                        pack_rows(static_cast<unsigned char*>(const_cast<void*>(dst.ref)), src.ref, src.n_ref, src.ld_ref, src.d, esz);
+                    memcpy(const_cast<double*>(dst.logl), src.logl, (size_t)src.n_query * 8);
+                    memcpy(const_cast<double*>(dst.weights), src.weights, (size_t)src.n_query * 8);
+                    ready[i].store(1, std::memory_order_release);
+                }
+            });
+        }
+    }
     std::vector<Pending> pend(n);
     int failed = -1, failed_rc = 0;
     for (int j = 0; j < n && failed < 0; ++j) {
         const int i = order[j];
         mce_ctx* lane = c->lanes[j % nl];
-        Run r{&problems[i], true, 0, nullptr, nullptr, &results[i], nullptr};
+        if (stage)
+            while (ready[i].load(std::memory_order_acquire) == 0) std::this_thread::yield();
+        Run r{stage ? &staged[i] : &problems[i], true, 0, nullptr, nullptr, &results[i], nullptr};
         r.hres = c->hres.as<DevScalars>() + i;
         r.batch_lane = true;
         pend[i].ev0 = c->ev_pool[2 * i];
@@ -1189,6 +1265,8 @@ int mce_evidence_batch(mce_ctx* c, int n, const mce_problem* problems, mce_resul
     }
     char first_err[sizeof(g_err)];
     snprintf(first_err, sizeof(first_err), "%s", g_err);
+    if (failed >= 0) next_job.store(n);      // nothing more to pack
+    for (auto& t : packers) t.join();
     for (int l = 0; l < nl; ++l) {
         const cudaError_t e = cudaStreamSynchronize(c->lanes[l]->stream);
         if (e != cudaSuccess && failed < 0) {

@@ -48,12 +48,21 @@ def evidence_many(chains, kmax=2, ndim=None, priorvolume=1.0, device=0, ctx=None
         import torch.distributed as dist
         rank, world = dist.get_rank(group), dist.get_world_size(group)
     mine = assign_largest_first([len(c) for c in chains], world)[rank]
-    probs = []
-    for i in mine:
+    def prepare(i):
+        # One strided pass over the chain for both leading columns (weight, -logL); the parameter block stays a view and
+        # is packed by the library's staging threads.  numpy releases the GIL in these copies, so chains are prepared
+        # concurrently.
         c = np.asarray(chains[i], dtype=np.float64)
         nd = c.shape[1] - 2 if ndims[i] is None else int(ndims[i])
-        probs.append({'query': c[:, 2:], 'logl': -c[:, 1], 'weights': c[:, 0], 'kmax': kmax, 'ndim': nd,
-                      'log_sum_w': math.log(np.sum(c[:, 0])), 'log_prior_volume': math.log(pvs[i])})
+        wl = np.ascontiguousarray(c[:, :2].T)
+        np.negative(wl[1], out=wl[1])
+        return {'query': c[:, 2:], 'logl': wl[1], 'weights': wl[0], 'kmax': kmax, 'ndim': nd,
+                'log_sum_w': math.log(np.sum(wl[0])), 'log_prior_volume': math.log(pvs[i])}
+
+    if len(mine) > 8:
+        probs = list(_prep_pool().map(prepare, mine))
+    else:
+        probs = [prepare(i) for i in mine]
     ctx = ctx or _lib.default_context(device)
     ctx.set_option('batch_lanes', max(1, min(int(nstreams), 32)))
     outs = ctx.evidence_batch(probs) if probs else []              # one C call: mce_evidence_batch
@@ -65,6 +74,18 @@ def evidence_many(chains, kmax=2, ndim=None, priorvolume=1.0, device=0, ctx=None
         for g in gathered:
             local.update(g)
     return [local[i][0] for i in range(n)], [local[i][1] for i in range(n)], [local[i][2] for i in range(n)]
+
+
+_PREP_POOL = None
+
+
+def _prep_pool():
+    global _PREP_POOL
+    if _PREP_POOL is None:
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        _PREP_POOL = ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1), thread_name_prefix='mce-prep')
+    return _PREP_POOL
 
 
 def _dist_ready():

@@ -206,6 +206,15 @@ def test_batch_lanes_match_single_calls():
                 np.testing.assert_array_equal(o['logE'], s1['logE'])
                 np.testing.assert_array_equal(o['var_logE'], s1['var_logE'])
                 assert o['log_jacobian'] == s1['log_jacobian']
+    ctx.set_option('batch_stage', 0)               # uploads straight from the caller's arrays: the same numbers
+    for o, s1 in zip(ctx.evidence_batch(probs), single):
+        np.testing.assert_array_equal(o['logE'], s1['logE'])
+    ctx.set_option('batch_stage', 1)
+    cross = [{'query': c[:len(c) // 2, 2:], 'ref': c[len(c) // 2:, 2:], 'logl': -c[:len(c) // 2, 1], 'weights': c[:len(c) // 2, 0],
+              'kmax': 2, 'ndim': d} for c, (_, d) in zip(chains[:5], shapes)]
+    for p, o in zip(cross, ctx.evidence_batch(cross)):
+        want = ctx.evidence(p['query'], p['logl'], p['weights'], 2, ref=p['ref'], ndim=p['ndim'])
+        np.testing.assert_array_equal(o['logE'], want['logE'])
     bad = np.column_stack((np.ones(50), np.zeros(50), np.ones((50, 2))))
     probs.insert(4, {'query': bad[:, 2:], 'logl': -bad[:, 1], 'weights': bad[:, 0], 'kmax': 3, 'ndim': 2})
     with pytest.raises(_lib.MCEError, match='problem 4'):
