@@ -143,6 +143,7 @@ struct mce_ctx {
     std::vector<mce_ctx*> lanes;
     std::vector<cudaEvent_t> ev_pool;   // start / end events of the problems of a batch
     int opt_lanes = 8;
+    int opt_tc_min_mpairs = 0;      // automatic engine choice: tcgen05 from this many million pairs on (0 = measured default)
     int opt_stage = 1;              // batches: pack the host arrays into a pinned arena on packer threads
     PinBuf hstage;
     int opt_sweep_seed = 1;         // sweep: one filter launch per chunk, seeded with the previous chunk's thresholds
@@ -482,7 +483,8 @@ int enqueue_problem(mce_ctx* c, const Run& r, Pending& pd) {
             // an explicit FFMA tiling option (tests, tuning runs) keeps the FFMA filter
             const bool ffma_tuned = c->opt_tq > 0 || c->opt_tr > 0 || c->opt_packed >= 0 || c->opt_sync >= 0;
             const double pairs = (double)nq * (double)n_ref;
-            use_tc = fits && !ffma_tuned && d >= 4 && pairs >= (d >= 10 ? 2e8 : 6e8);
+            const double min_pairs = c->opt_tc_min_mpairs > 0 ? 1e6 * c->opt_tc_min_mpairs : (d >= 10 ? 2e8 : 6e8);
+            use_tc = fits && !ffma_tuned && d >= 4 && pairs >= min_pairs;
         }
     }
     if (use_tc) {
@@ -1067,6 +1069,7 @@ int mce_ctx_set_option(mce_ctx* c, const char* name, int value) {
     else if (!strcmp(name, "tail_chunks")) c->opt_tail = value;
     else if (!strcmp(name, "sweep_seed")) c->opt_sweep_seed = value != 0;
     else if (!strcmp(name, "batch_stage")) c->opt_stage = value != 0;
+    else if (!strcmp(name, "tc_min_mpairs")) c->opt_tc_min_mpairs = value > 0 ? value : 0;
     else if (!strcmp(name, "batch_lanes")) {
         if (value < 1 || value > 32) return fail(MCE_ERR_ARG, "batch_lanes must be in [1, 32]");
         c->opt_lanes = value;
@@ -1173,6 +1176,7 @@ int mce_evidence_batch(mce_ctx* c, int n, const mce_problem* problems, mce_resul
         lane->opt_margin = c->opt_margin; lane->opt_sync = c->opt_sync; lane->opt_tail = c->opt_tail;
         lane->opt_engine = c->opt_engine; lane->opt_tc_slack = c->opt_tc_slack; lane->opt_tc_stages = c->opt_tc_stages;
         lane->opt_tc_mma_warps = c->opt_tc_mma_warps;
+        lane->opt_tc_min_mpairs = c->opt_tc_min_mpairs;
         lane->share = nl;
     }
     // Host staging.  A copy from pageable memory waits for the lane's stream and goes through the driver's own bounce
