@@ -189,7 +189,9 @@ def test_batch_lanes_match_single_calls():
     """mce_evidence_batch overlaps problems on internal streams: results equal n mce_evidence calls bit for bit,
     whatever the number of lanes, and a failing problem is named."""
     from mcevidence_b200 import _lib
-    shapes = [(1475, 6), (9000, 7), (3000, 8), (2200, 9), (4000, 7), (700, 6), (15000, 6), (5100, 9), (800, 7), (12000, 8)]
+    # two cells large enough for the tcgen05 engine (>= 6e8 pairs) run on lanes next to FFMA-engine cells
+    shapes = [(1475, 6), (9000, 7), (3000, 8), (2200, 9), (4000, 7), (700, 6), (15000, 6), (5100, 9), (800, 7), (12000, 8),
+              (30000, 7), (26000, 9)]
     chains = [gaussian_chain(n, d, seed=130 + i, integer_weights=True, inflate=1.0, nextra=3)[0]
               for i, (n, d) in enumerate(shapes)]
     probs = [{'query': c[:, 2:], 'logl': -c[:, 1], 'weights': c[:, 0], 'kmax': 3, 'ndim': d,
@@ -198,6 +200,7 @@ def test_batch_lanes_match_single_calls():
     ctx = _lib.Context(0)
     single = [ctx.evidence(p['query'], p['logl'], p['weights'], 3, ndim=p['ndim'], log_sum_w=p['log_sum_w'],
                            log_prior_volume=p['log_prior_volume']) for p in probs]
+    assert single[-1]['stats']['filter_mode'] == 16 and single[0]['stats']['filter_mode'] != 16
     for lanes in (1, 3, 8):
         ctx.set_option('batch_lanes', lanes)
         for rep in range(2):                       # second pass: warm workspaces
