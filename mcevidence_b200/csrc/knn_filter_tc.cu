@@ -1,23 +1,25 @@
-// K2-TC: tensor-core engine of the neighbour filter (tcgen05 + TMEM + TMA, sm_100a).  Opt-in
-// ("filter_engine" = 1); the FFMA filter of knn_filter.cuh stays the default until this engine has
-// been validated on hardware.
+// K2-TC: tensor-core engine of the neighbour filter (tcgen05 + TMEM + TMA, sm_100a).  Validated on B200 (bit-identical
+// neighbours and logE: tests/test_gpu_tc.py and the whole GPU suite) and chosen automatically for ndim >= 4 from ~6e8
+// pairs on ("filter_engine" = 2, the default; 1 forces it, 0 forces the FFMA filter of knn_filter.cuh).
 //
 // Replaces the same reference step as the FFMA filter, the neighbour search of
 // NearestNeighbors.kneighbors (MCEvidence.py:1104), and writes the same candidate planes, so the
 // FP64 re-rank / verification (K3) is shared.
 //
-// One CTA = one (query block of 256, reference range) unit, 10 warps:
-//   warps 0-7  epilogue: warp w owns TMEM lane quadrant w%4 of query block w/4; thread = one query
-//   warp  8    TMA producer: one bulk copy per 128-reference tile into a shared-memory ring
-//   warp  9    MMA issuer: per tile 2 x K/8 tcgen05.mma.kind::tf32 (M=128 queries x N=128
-//              references) into one of two TMEM accumulator buffers, one tcgen05.commit per query block
+// One CTA = one (query block of 256, reference range) unit, 20 warps:
+//   warps 0-15 epilogue: warp w owns TMEM lane quadrant w%4 of query block (w/4)%2 and column half w/8;
+//              thread = one query, 64 columns of every tile
+//   warp  16   TMA producer: one bulk copy per 128-reference tile into a shared-memory ring
+//   warps 17-18 MMA issuers (even / odd tiles): per tile 2 query blocks x K/8 tcgen05.mma.kind::tf32 (M=128 queries x
+//              N=128 references) into one of two TMEM accumulator buffers, one tcgen05.commit per tile
+//   warp  19   selection: pops the hits from a shared-memory queue, evaluates them exactly, owns the top-L lists
 // A row = [q_0..q_{d-1}, 1, 1, 0..], B row = [r_0..r_{d-1}, h_hi, h_lo, 0..] with h = -|r|^2/2, so
 // the accumulator holds the ranking score s = q.r - |r|^2/2 of the FFMA filter, evaluated with
 // TF32-truncated operands ("coarse").  Both operand tiles keep the full FP32 words; the tensor
 // core ignores the low 13 mantissa bits.
 //
-// Selection.  The epilogue reads 32 accumulator columns per tcgen05.ld, takes their maximum
-// (FMNMX3 tree, about half an ALU instruction per pair) and compares it with th - e, where th is
+// Selection.  An epilogue thread reads its 64 accumulator columns with one tcgen05.ld, takes the maximum of each
+// 32-column group (FMNMX3 tree, about half an ALU instruction per pair) and compares it with th - e, where th is
 // the query's current threshold (minimum of its top-L list) and e bounds |coarse - exact| for
 // every reference (operand truncation 2^-10 each, h split into a TF32-exact head and a remainder,
 // generous allowance for the accumulation inside the tensor core).  Only columns that pass are
