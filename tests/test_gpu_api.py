@@ -180,6 +180,16 @@ def test_batch_size_sweep_is_bit_identical(engine, cross):
     want = O.evidence(s[:900], logl[:900], w[:900], d, kmax, s2=ref, knn='brute', cov_from=c[:, 2:] if cross else s,
                       sum_w=w.sum())
     assert np.abs(got2[0]['logE'] - want).max() < 1e-9
+    # the largest batch may be smaller than the chain: rows beyond it are neither searched nor uploaded (explicit W) ...
+    part = ctx.evidence_sweep(s, logl, w, kmax, [700, 2000], ref=ref, **kw)
+    for nb, g in zip((700, 2000), part):
+        np.testing.assert_array_equal(g['logE'], ctx.evidence(s[:nb], logl[:nb], w[:nb], kmax, ref=ref, **kw)['logE'])
+    # ... but still enter the covariance when the library estimates it (covtype='all')
+    part2 = ctx.evidence_sweep(s, logl, w, kmax, [800, 2100], ref=ref, ndim=d, log_sum_w=math.log(w.sum()))
+    for nb, g in zip((800, 2100), part2):
+        want = O.evidence(s[:nb], logl[:nb], w[:nb], d, kmax, s2=ref, knn='brute', cov_from=c[:, 2:] if cross else s,
+                          sum_w=w.sum())
+        assert np.abs(g['logE'] - want).max() < 1e-9
     with pytest.raises(_lib.MCEError):
         ctx.evidence_sweep(s, logl, w, kmax, [3], ref=None if not cross else ref[:2], **kw)   # fewer rows than neighbours
     ctx.close()
