@@ -476,6 +476,17 @@ def _measured_tf32_peak():
         return 1125.0, 'nominal 2250 TFLOP/s bf16 / 2 (MEASURED_PEAKS.json not found)'
 
 
+def _alu_floor(ctx, pairs, t_k2):
+    """Time the FMNMX3 max tree of the tcgen05 epilogue would need alone at the measured FMNMX3 rate."""
+    try:
+        rate = max(ctx.unit_peak(0, 4096)[0] for _ in range(3))          # lane-operations per second
+        floor_s = pairs * 17.0 / 32.0 / rate
+        return {'fmnmx3_lane_ops_per_s': rate, 'lane_ops_per_pair': 17.0 / 32.0, 'floor_ms': 1e3 * floor_s,
+                'frac': floor_s / t_k2}
+    except Exception as exc:                                               # diagnostics only
+        return {'error': str(exc)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -661,6 +672,9 @@ def main():
                              'kernel': 'knn_filter_tc_kernel<KSTEPS=%d>' % (kpad // 8), 'peak_source': tf32_peak[1],
                              'fma_pipe_frac': None, 'executed_fma_tflops': None,
                              'algorithmic_frac_of_fp32_fma_peak': achieved / FP32_PEAK_THEORETICAL_TFLOPS,
+                             # the unit that actually binds this kernel is the ALU pipe of the epilogue: 17 FMNMX3 per 32
+                             # scores; its peak is measured live with the kernel's own instruction (mce_unit_peak 0)
+                             'epilogue_alu': _alu_floor(ctx, pairs_launch, t_k2),
                              'note': 'achieved = executed TF32 MMA FLOP (2 K per pair, K = %d for ndim %d) against half the '
                                      'measured bf16 peak; algorithmic_tflops = 3d FLOP per pair (SURVEY 8d M4), beside it as '
                                      'a fraction of the theoretical FP32 FMA peak the CUDA-core filter is bounded by' % (kpad, d)})

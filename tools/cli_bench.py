@@ -54,13 +54,30 @@ def cpu_port():
                       n_jobs=-1, scalar_loop=True)
 
 
-cpu_port()
+from oracle import ref_loader                           # noqa: E402
+
+
+def reference_cli():
+    """The UNMODIFIED reference on the same files: its own file reader, burn-in, params_info and evidence()."""
+    import logging
+    R = ref_loader.load()
+    logging.disable(logging.CRITICAL)
+    try:
+        par = R.params_info(root, cosmo=True)
+        return R.MCEvidence(root, ndim=par['ndim'], priorvolume=par['volume'], kmax=2, burnlen=0.3, verbose=0).evidence(nproc=-1)
+    finally:
+        logging.disable(logging.NOTSET)
+
+
+kind = 'reference' if ref_loader.available() else 'port'
+run_cpu = reference_cli if kind == 'reference' else cpu_port
+run_cpu()
 t_cpu = []
 for _ in range(max(2, a.reps // 2)):
     t0 = time.perf_counter()
-    want = cpu_port()
+    want = run_cpu()
     t_cpu.append(time.perf_counter() - t0)
 print(json.dumps({'workload': 'cfg1 shape: 4 chains x %d rows x %d columns, ndim 6, kmax 2, burn 0.3' % (a.rows, 8 + a.extra),
-                  'ours_cli_s_best': min(t_gpu), 'ours_cli_s_all': t_gpu, 'cpu_port_s_best': min(t_cpu),
-                  'cpu_cores': os.cpu_count(), 'logE': float(mle[0]), 'abs_diff_vs_cpu_port': float(abs(mle[0] - want[0])),
+                  'ours_cli_s_best': min(t_gpu), 'ours_cli_s_all': t_gpu, 'cpu_s_best': min(t_cpu), 'cpu_kind': kind,
+                  'cpu_cores': os.cpu_count(), 'logE': float(mle[0]), 'abs_diff_vs_cpu': float(abs(mle[0] - np.ravel(want)[0])),
                   'file_mb': sum(os.path.getsize('%s_%d.txt' % (root, i + 1)) for i in range(4)) / 1e6}))
