@@ -393,3 +393,32 @@ def test_full_size_properties_cfg5_shape(ctx):
     size class of the 8-GPU scaling run."""
     out = _full_size_properties(ctx, 2000000, 20, 8, False, seed=5, nspot=32, nshard=2000)
     assert out['stats']['filter_mode'] == 16
+
+
+@pytest.mark.parametrize('engine', [0, 1])
+def test_random_shapes_bit_exact(engine):
+    """Thirty seeded random (n, ndim, k, auto / cross) problems per filter engine, with anisotropic, shifted and partly
+    duplicated data: neighbour indices and distances bit for bit against the FP64 oracle (MCEvidence.py:1104)."""
+    from mcevidence_b200 import _lib
+    ctx = _lib.Context(0)
+    ctx.set_option('filter_engine', engine)
+    rng = np.random.default_rng(20261017)
+    for case in range(30):
+        n = int(rng.integers(20, 3500))
+        d = int(rng.integers(1, 41))
+        cross = bool(rng.integers(0, 2))
+        nref = int(rng.integers(20, 3500)) if cross else n
+        k = int(rng.integers(2, min(10, nref - 1) + 1))
+        scale = np.exp(rng.normal(size=d))
+        x = rng.normal(size=(n, d)) * scale + rng.normal(size=d) * 3.0
+        ref = (rng.normal(size=(nref, d)) * scale + rng.normal(size=d) * 3.0) if cross else None
+        if case % 5 == 0:                      # exact duplicates: ties are ordered by index
+            x[n // 2:n // 2 + 5] = x[:5]
+        if engine == 1 and d > 62:
+            continue
+        dk, ix, st = ctx.knn(x, k, ref=ref, identity=True)
+        od, oi = oracle_knn(x, k, ref)
+        assert np.array_equal(ix, oi), (case, n, d, k, cross)
+        assert np.array_equal(dk, od), (case, n, d, k, cross)
+        assert (st['filter_mode'] == 16) == (engine == 1)
+    ctx.close()
