@@ -181,11 +181,16 @@ __global__ void __launch_bounds__(128) whiten_kernel(Segment x, int d, const dou
             j = (int)(row - tile * TJ);
             tb = tiles + tile * (long long)((d + 1) * TJ);
         }
+        // The centred row is read once (d strided loads per thread) into a per-thread array -- local memory, which is
+        // interleaved per thread and therefore coalesced -- instead of d times d scattered loads; same arithmetic.
+        double xr[MAX_DIM];
+        if (valid)
+            for (int a = 0; a < d; ++a) xr[a] = x.at(xrow, a) - smu[a];
         double n2 = 0.0;
         for (int c = 0; c < d; ++c) {
             double y = 0.0;
             if (valid) {
-                for (int a = 0; a < d; ++a) y += (x.at(xrow, a) - smu[a]) * sw[a * d + c];
+                for (int a = 0; a < d; ++a) y += xr[a] * sw[a * d + c];
                 y64[row * d + c] = y;
             }
             if (tb) tb[(c + 1) * TJ + j] = (float)y;
