@@ -24,6 +24,45 @@ __device__ __forceinline__ double seg_at(const Segment& a, const Segment& b, lon
 // Rows per staged chunk so that the chunk fits 32 KB of shared memory.
 __host__ __device__ inline int cov_chunk_rows(int d) { return 4096 / d; }
 
+// Stage rows [r0, r0 + nr) of a U b, first d columns (minus `shift` when given), into shared memory, element e = r d + c.
+// (row, column) advance incrementally -- no division per element -- and four loads are in flight per thread.
+__device__ __forceinline__ void cov_stage_rows(const Segment& a, const Segment& b, long long r0, int nr, int d,
+                                               const double* shift, double* xs) {
+    const int total = nr * d;
+    const int dr = COV_THREADS / d, dc = COV_THREADS - dr * d;   // one stride of COV_THREADS elements = dr rows + dc columns
+    int r = threadIdx.x / d, c = threadIdx.x - r * d;
+    int e = threadIdx.x;
+    for (; e + 3 * COV_THREADS < total; e += 4 * COV_THREADS) {
+        int rr[4], cc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            rr[u] = r;
+            cc[u] = c;
+            r += dr;
+            c += dc;
+            if (c >= d) {
+                c -= d;
+                ++r;
+            }
+        }
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = seg_at(a, b, r0 + rr[u], cc[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xs[e + u * COV_THREADS] = shift ? v[u] - shift[cc[u]] : v[u];
+    }
+    for (; e < total; e += COV_THREADS) {
+        const double v = seg_at(a, b, r0 + r, c);
+        xs[e] = shift ? v - shift[c] : v;
+        r += dr;
+        c += dc;
+        if (c >= d) {
+            c -= d;
+            ++r;
+        }
+    }
+}
+
 // pass 1: per-CTA column sums
 __global__ void __launch_bounds__(COV_THREADS) colsum_kernel(Segment a, Segment b, int d, double* partial) {
     __shared__ double xs[4096];
@@ -32,10 +71,7 @@ __global__ void __launch_bounds__(COV_THREADS) colsum_kernel(Segment a, Segment 
     double acc = 0.0;
     for (long long r0 = (long long)blockIdx.x * rc; r0 < n; r0 += (long long)gridDim.x * rc) {
         const int nr = (int)min((long long)rc, n - r0);
-        for (int e = threadIdx.x; e < nr * d; e += COV_THREADS) {
-            const int r = e / d, c = e - r * d;
-            xs[e] = seg_at(a, b, r0 + r, c);
-        }
+        cov_stage_rows(a, b, r0, nr, d, nullptr, xs);
         __syncthreads();
         if (threadIdx.x < d)
             for (int r = 0; r < nr; ++r) acc += xs[r * d + threadIdx.x];
@@ -75,10 +111,7 @@ __global__ void __launch_bounds__(COV_THREADS) scatter_kernel(Segment a, Segment
     __syncthreads();
     for (long long r0 = (long long)blockIdx.x * rc; r0 < n; r0 += (long long)gridDim.x * rc) {
         const int nr = (int)min((long long)rc, n - r0);
-        for (int e = threadIdx.x; e < nr * d; e += COV_THREADS) {
-            const int r = e / d, c = e - r * d;
-            xs[e] = seg_at(a, b, r0 + r, c) - smean[c];
-        }
+        cov_stage_rows(a, b, r0, nr, d, smean, xs);
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < COV_PAIRS_PER_THREAD; ++i) {
