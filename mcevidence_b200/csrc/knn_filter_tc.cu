@@ -192,6 +192,41 @@ __device__ __forceinline__ float tc_exact_score_g(uint32_t arow, const float* __
     return acc;
 }
 
+// Two (query, reference) pairs per lane: the loads of both reference rows are issued before the first FMA, so the pair
+// shares one L2 round trip (selection warp, batches of 64 hits).
+template <int KSTEPS>
+__device__ __forceinline__ void tc_exact_score_g2(const uint32_t (&arow)[2], const float* const (&brow)[2], int d, float (&acc)[2]) {
+    constexpr int NC = 2 * KSTEPS;
+    constexpr int CH = NC < 4 ? NC : 4;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+        acc[j] = __ldg(brow[j] + (d >> 2) * TC_CHUNK_FLOATS + (d & 3)) +
+                 __ldg(brow[j] + ((d + 1) >> 2) * TC_CHUNK_FLOATS + ((d + 1) & 3));   // h_hi + h_lo == h exactly
+#pragma unroll
+    for (int c0 = 0; c0 < NC; c0 += CH) {
+        float4 bv[2][CH];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int c = 0; c < CH; ++c)
+                if (c0 + c < NC) bv[j][c] = __ldg(reinterpret_cast<const float4*>(brow[j] + (c0 + c) * TC_CHUNK_FLOATS));
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                if (c0 + c < NC) {
+                    const float4 av = lds_f32x4(arow[j] + (c0 + c) * TC_CHUNK_BYTES);
+                    const int k = 4 * (c0 + c);
+                    if (k < d) acc[j] = fmaf(av.x, bv[j][c].x, acc[j]);
+                    if (k + 1 < d) acc[j] = fmaf(av.y, bv[j][c].y, acc[j]);
+                    if (k + 2 < d) acc[j] = fmaf(av.z, bv[j][c].z, acc[j]);
+                    if (k + 3 < d) acc[j] = fmaf(av.w, bv[j][c].w, acc[j]);
+                }
+            }
+        }
+    }
+}
+
 // hit queue: epilogue lanes push (query, reference), the selection warp pops.  A slot holds TC_QEMPTY or an item, so
 // the slot itself says when its content is valid; `head` is published by the consumer after it has emptied slots.
 struct TcQueue {
@@ -499,7 +534,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
             }
         }
     } else if (warp == TC_SELECT_WARP) {
-        // Selection warp: pops up to 32 hits at a time, evaluates them exactly (one lane each: query row from the A
+        // Selection warp: pops up to 64 hits at a time, evaluates them exactly (two per lane: query row from the A
         // tile, reference row from the image in L2) and maintains the lists and thresholds of all 256 queries.
         const uint32_t ctrl = queue.ctrl;
         const float* img = p.tiles;
@@ -515,50 +550,77 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
                 __nanosleep(64);
                 continue;
             }
-            // pop the written prefix of the next 32 positions: a reserved slot may not have been written yet, and its
-            // owner may be held up by warp-mates that wait for `head` to move, so never wait for a slot here
-            const uint32_t nres = avail < 32u ? avail : 32u;
-            unsigned long long item = TC_QEMPTY;
-            const uint32_t addr = queue.items + ((head + lane) & (TC_QCAP - 1)) * 8u;
-            if ((uint32_t)lane < nres) item = lds_u64_volatile(addr);
-            const uint32_t unwritten = __ballot_sync(0xffffffffu, item == TC_QEMPTY);
-            const uint32_t n = unwritten ? (uint32_t)(__ffs((int)unwritten) - 1) : 32u;
+            // pop the written prefix of the next 64 positions, two per lane (lane l: positions l and 32 + l) -- the exact
+            // evaluation waits for one L2 round trip per batch, so a batch of 64 costs little more than one of 32.  A
+            // reserved slot may not have been written yet, and its owner may be held up by warp-mates that wait for
+            // `head` to move, so never wait for a slot here.
+            const uint32_t nres = avail < 64u ? avail : 64u;
+            unsigned long long item[2] = {TC_QEMPTY, TC_QEMPTY};
+            uint32_t addr[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                addr[j] = queue.items + ((head + 32u * j + lane) & (TC_QCAP - 1)) * 8u;
+                if (32u * j + (uint32_t)lane < nres) item[j] = lds_u64_volatile(addr[j]);
+            }
+            const uint32_t unw0 = __ballot_sync(0xffffffffu, (uint32_t)lane < nres && item[0] == TC_QEMPTY);
+            const uint32_t unw1 = __ballot_sync(0xffffffffu, 32u + (uint32_t)lane < nres && item[1] == TC_QEMPTY);
+            const uint32_t n = unw0 ? (uint32_t)(__ffs((int)unw0) - 1) : unw1 ? 32u + (uint32_t)(__ffs((int)unw1) - 1) : nres;
             if (n == 0u) {
                 if ((++idle & 255u) == 0u && *reinterpret_cast<volatile unsigned int*>(&g_tc_stuck[0]) != 0u) break;
                 __nanosleep(32);
                 continue;
             }
-            const bool has = (uint32_t)lane < n;
-            if (has) sts_u64_volatile(addr, TC_QEMPTY);
+            bool has[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                has[j] = 32u * j + (uint32_t)lane < n;
+                if (has[j]) sts_u64_volatile(addr[j], TC_QEMPTY);
+            }
             head += n;
             __threadfence_block();
             __syncwarp();
             if (lane == 0) sts_u32_volatile(ctrl + 4, head);
-            const uint32_t q = has ? (uint32_t)(item >> 32) : 0u;
-            const int ridx = has ? (int)(uint32_t)item : 0;
-            float s = -CUDART_INF_F;
-            if (has) {
-                const uint32_t arow = smem_u32(a_sm) + (q >> 7) * A_MB_BYTES + ((q & 127u) >> 3) * TC_ROWGROUP_BYTES + (q & 7u) * 16u;
-                const float* brow = img + (size_t)(ridx >> 7) * (K * TC_TILE_REFS) + ((ridx & 127) >> 3) * 32 + (ridx & 7) * 4;
-                s = tc_exact_score_g<KSTEPS>(arow, brow, d);
-                const int self = p.self_exclude ? (int)(p.q_begin + (long long)qblock * TC_QUERIES + q + p.self_offset) : -0x7fffffff;
-                if (ridx == self) s = -CUDART_INF_F;
+            uint32_t q[2];
+            int ridx[2];
+            float s[2];
+            uint32_t arow[2];
+            const float* brow[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                q[j] = has[j] ? (uint32_t)(item[j] >> 32) : 0u;
+                ridx[j] = has[j] ? (int)(uint32_t)item[j] : 0;
+                arow[j] = smem_u32(a_sm) + (q[j] >> 7) * A_MB_BYTES + ((q[j] & 127u) >> 3) * TC_ROWGROUP_BYTES + (q[j] & 7u) * 16u;
+                brow[j] = img + (size_t)(ridx[j] >> 7) * (K * TC_TILE_REFS) + ((ridx[j] & 127) >> 3) * 32 + (ridx[j] & 7) * 4;
             }
-            // hits of the same query are inserted one after the other (rank within the batch)
-            const uint32_t peers = __match_any_sync(0xffffffffu, has ? q : (0x80000000u | (uint32_t)lane));
-            const int rank = __popc(peers & ((1u << lane) - 1u));
-            const int maxrank = __reduce_max_sync(0xffffffffu, rank);
-            for (int r = 0; r <= maxrank; ++r) {
-                if (has && rank == r) {
-                    const uint32_t tha = smem_u32(th_s) + q * 4u;
-                    const float th = lds_f32(tha);
-                    if (s > th) {
-                        const uint32_t lsa = smem_u32(ls) + q * 4u, lia = smem_u32(li) + q * 4u;
-                        const float nmin = L <= 8 ? tc_list_insert<8>(lsa, lia, L, s, ridx) : tc_list_insert<TC_LMAX>(lsa, lia, L, s, ridx);
-                        sts_f32(tha, fmaxf(th, nmin));   // the bootstrap floor stays in force while the list fills
+            tc_exact_score_g2<KSTEPS>(arow, brow, d, s);   // both rows' loads in flight together (idle lanes read row 0)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int self = p.self_exclude ? (int)(p.q_begin + (long long)qblock * TC_QUERIES + q[j] + p.self_offset) : -0x7fffffff;
+                if (!has[j] || ridx[j] == self) s[j] = -CUDART_INF_F;
+            }
+            // hits of the same query are inserted one after the other (rank within the half-batch, first half first)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (j == 1 && n <= 32u) continue;
+                const bool hj = has[j];
+                const uint32_t qj = q[j];
+                const float sj = s[j];
+                const int rj = ridx[j];
+                const uint32_t peers = __match_any_sync(0xffffffffu, hj ? qj : (0x80000000u | (uint32_t)lane));
+                const int rank = __popc(peers & ((1u << lane) - 1u));
+                const int maxrank = __reduce_max_sync(0xffffffffu, rank);
+                for (int r = 0; r <= maxrank; ++r) {
+                    if (hj && rank == r) {
+                        const uint32_t tha = smem_u32(th_s) + qj * 4u;
+                        const float th = lds_f32(tha);
+                        if (sj > th) {
+                            const uint32_t lsa = smem_u32(ls) + qj * 4u, lia = smem_u32(li) + qj * 4u;
+                            const float nmin = L <= 8 ? tc_list_insert<8>(lsa, lia, L, sj, rj) : tc_list_insert<TC_LMAX>(lsa, lia, L, sj, rj);
+                            sts_f32(tha, fmaxf(th, nmin));   // the bootstrap floor stays in force while the list fills
+                        }
                     }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     } else {
