@@ -469,7 +469,7 @@ int enqueue_problem(mce_ctx* c, const Run& r, Pending& pd) {
         yq_base = c->yr.as<double>();
     }
     // engine 2 = automatic (the default): the tcgen05 engine where it was measured faster than the FFMA filter on B200
-    // (profiles/r02_engine_sweep.json): ndim >= 4 and at least ~6e8 pairs (2e8 from ndim 10 on).  Below that the
+    // (profiles/r02_engine_sweep.json): ndim >= 4 and at least ~3e8 pairs (tools/small_probe.py, midsize_probe.py).  Below that the
     // 256-query x 128-reference tiles of one CTA per SM cannot fill the GPU, and for ndim <= 3 the TF32 allowance
     // admits too many false candidates.
     bool use_tc = false;
@@ -483,7 +483,7 @@ int enqueue_problem(mce_ctx* c, const Run& r, Pending& pd) {
             // an explicit FFMA tiling option (tests, tuning runs) keeps the FFMA filter
             const bool ffma_tuned = c->opt_tq > 0 || c->opt_tr > 0 || c->opt_packed >= 0 || c->opt_sync >= 0;
             const double pairs = (double)nq * (double)n_ref;
-            const double min_pairs = c->opt_tc_min_mpairs > 0 ? 1e6 * c->opt_tc_min_mpairs : (d >= 10 ? 2e8 : 6e8);
+            const double min_pairs = c->opt_tc_min_mpairs > 0 ? 1e6 * c->opt_tc_min_mpairs : 3e8;
             use_tc = fits && !ffma_tuned && d >= 4 && pairs >= min_pairs;
         }
     }

@@ -1,5 +1,5 @@
 // K2-TC: tensor-core engine of the neighbour filter (tcgen05 + TMEM + TMA, sm_100a).  Validated on B200 (bit-identical
-// neighbours and logE: tests/test_gpu_tc.py and the whole GPU suite) and chosen automatically for ndim >= 4 from ~6e8
+// neighbours and logE: tests/test_gpu_tc.py and the whole GPU suite) and chosen automatically for ndim >= 4 from ~3e8
 // pairs on ("filter_engine" = 2, the default; 1 forces it, 0 forces the FFMA filter of knn_filter.cuh).
 //
 // Replaces the same reference step as the FFMA filter, the neighbour search of

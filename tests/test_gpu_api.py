@@ -199,7 +199,7 @@ def test_batch_lanes_match_single_calls():
     """mce_evidence_batch overlaps problems on internal streams: results equal n mce_evidence calls bit for bit,
     whatever the number of lanes, and a failing problem is named."""
     from mcevidence_b200 import _lib
-    # two cells large enough for the tcgen05 engine (>= 6e8 pairs) run on lanes next to FFMA-engine cells
+    # two cells large enough for the tcgen05 engine (>= 3e8 pairs) run on lanes next to FFMA-engine cells
     shapes = [(1475, 6), (9000, 7), (3000, 8), (2200, 9), (4000, 7), (700, 6), (15000, 6), (5100, 9), (800, 7), (12000, 8),
               (30000, 7), (26000, 9)]
     chains = [gaussian_chain(n, d, seed=130 + i, integer_weights=True, inflate=1.0, nextra=3)[0]
