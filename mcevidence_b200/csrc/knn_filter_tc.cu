@@ -30,6 +30,21 @@
 #include "knn_filter.cuh"
 #include "tcgen05.cuh"
 #include <math_constants.h>
+#include <type_traits>
+
+// Development switches: variants are built with -D (tools/build_variant.sh) and compared on one GPU box (tools/tc_ab.py).
+#ifndef TC_SLAB
+#define TC_SLAB 1           // 1: after the start-up tiles a hit lane only spills its 32 coarse scores (fire and forget)
+#endif
+#ifndef TC_SLAB_T0
+#define TC_SLAB_T0 300      // x list length = tiles of a unit that keep the column-precise hit path: about 350 x L / t hits per
+#endif                      // tile reach the selection warp, which handles ~2 slab events per tile time (profiles/r02_tc_ab_*.jsonl)
+#ifndef TC_SEL_MIN
+#define TC_SEL_MIN 32       // the selection warp evaluates a batch when at least this many hits are waiting
+#endif
+#ifndef TC_PROBE
+#define TC_PROBE 0          // 1: count hits and the clocks spent in the hit path / in the selection warp (mce_tc_probe)
+#endif
 
 namespace mce {
 
@@ -99,6 +114,11 @@ __device__ __forceinline__ uint32_t atoms_add_u32(uint32_t a, uint32_t v) {
     asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
     return old;
 }
+__device__ __forceinline__ void sts_b32x4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void reds_or_u32(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void reds_and_u32(uint32_t a, uint32_t v) { asm volatile("red.shared.and.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
@@ -110,6 +130,21 @@ constexpr int TC_LMAX = MCE_TC_LIST_MAX;              // longest list: KCAP neig
 constexpr int TC_BOOT = 9;                            // bootstrap network: the 9 largest coarse scores of a unit's first tile
 constexpr uint32_t TC_QCAP = 512;                     // hit-queue slots (power of two)
 constexpr unsigned long long TC_QEMPTY = 0xFFFFFFFFFFFFFFFFull;
+// TC_PROBE builds: [0] hit-path entries (lanes), [1] clocks inside, [2] entries that found their slab taken, [3] clocks of
+// the column-precise path, [4] its entries, [5] batches evaluated, [6] items in them, [7] clocks of the evaluations,
+// [8] slab events, [9] clocks of the slab gathering
+static __device__ unsigned long long g_tc_probe[64];   // [16..39] / [40..63]: log2 histograms of the slab / scan path clocks
+#if TC_PROBE
+#define TC_PROBE_ADD(i, v) atomicAdd(&g_tc_probe[i], (unsigned long long)(v))
+#else
+#define TC_PROBE_ADD(i, v) do { } while (0)
+#endif
+// Slab path (TC_SLAB): one 128-byte slab per epilogue thread for the 32 coarse scores of a passing column group, a header
+// word per thread (0 = slab free, else 0x80000000 | index of the group's first reference) and one "pending lanes" word
+// per epilogue warp.  Only for K <= 40 (ndim <= 38): beyond that the operand tiles need the shared memory.
+constexpr int TC_SLAB_MAX_KSTEPS = 5;
+constexpr size_t TC_SLAB_BYTES = (size_t)TC_EPI_WARPS * 32 * (128 + 4) + TC_EPI_WARPS * 4 + TC_QUERIES * 4 + 96 * 8;
+__host__ __device__ constexpr bool tc_slab_on(int ksteps) { return TC_SLAB != 0 && ksteps <= TC_SLAB_MAX_KSTEPS; }
 
 // Replace the minimum of the list of one query; the caller guarantees s > current minimum.  Returns the new
 // minimum = new threshold.  All entries are loaded before the first comparison (one shared-memory latency).
@@ -275,12 +310,13 @@ struct TcEpiState {
     uint32_t full_bar, full_parity;   // "TMA bytes landed" barrier of the tile being processed
     int d;
     float* dump_row;     // where this query's coarse scores of the unit's first tile go (or null)
+    uint32_t slab0;      // slab path: shared address of the slab area (slabs, header words, pending-lanes words)
 };
 
 // One accumulator half-tile of a query: 64 coarse scores in registers (the TMEM buffer has already been released).
 // The maxima of the two 32-column groups (2 x 17 FMNMX) are compared with the query's cut; only then (rare) the
 // passing columns are collected in bit masks and pushed to the hit queue.
-template <int KSTEPS, bool CHECK>
+template <int KSTEPS, bool CHECK, bool USE_SLAB>
 __device__ __forceinline__ void tc_process_tile(const uint32_t (&v)[TC_HALF_COLS], uint32_t tile, int col_base, int ridx0, float tcut,
                                                 uint32_t query, const TcQueue& q, TcEpiState& st) {
     if constexpr (CHECK) {
@@ -309,23 +345,83 @@ __device__ __forceinline__ void tc_process_tile(const uint32_t (&v)[TC_HALF_COLS
 #pragma unroll
     for (int g = 0; g < 2; ++g) m[g] = max32(&v[32 * g]);
     if (fmaxf(m[0], m[1]) > tcut) {
-        uint32_t mask[2];
+        // The pipeline has no slack: whatever this warp spends here, all twenty wait for two tiles later (measured: the
+        // cost of a hit is the LATENCY of this path, not its instruction count and not the selection warp's time).
+#if TC_PROBE
+        const long long pc0 = clock64();
+#endif
+        if constexpr (USE_SLAB) {
+            // Stores and a reduction only -- nothing this lane waits for, unless its slab is still taken (rare).  The
+            // selection warp finds the passing columns in the slab.
+            const uint32_t slab = st.slab0 + threadIdx.x * 128u, hdr = st.slab0 + TC_EPI_WARPS * 32 * 128 + threadIdx.x * 4u;
+            const uint32_t pend = st.slab0 + TC_EPI_WARPS * 32 * 132 + (threadIdx.x >> 5) * 4u;
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            mask[g] = 0u;
-            if (m[g] > tcut) {
+            for (int g = 0; g < 2; ++g) {
+                if (m[g] > tcut) {
+                    long long t0 = 0;
+#if TC_PROBE
+                    if (lds_u32_volatile(hdr) != 0u) TC_PROBE_ADD(2, 1);
+#endif
+                    for (unsigned int it = 1u; lds_u32_volatile(hdr) != 0u; ++it) {
+                        __nanosleep(32);
+                        if ((it & 255u) == 0u) {
+                            if (*reinterpret_cast<volatile unsigned int*>(&g_tc_stuck[0]) != 0u) break;
+                            const long long now = clock64();
+                            if (t0 == 0) {
+                                t0 = now;
+                            } else if (now - t0 > 1000000000LL) {
+                                if (atomicCAS(&g_tc_stuck[0], 0u, 3u) == 0u) {
+                                    g_tc_stuck[1] = hdr;
+                                    g_tc_stuck[2] = threadIdx.x;
+                                    g_tc_stuck[3] = blockIdx.x;
+                                }
+                                break;
+                            }
+                        }
+                    }
 #pragma unroll
-                for (int i = 0; i < 32; ++i) mask[g] |= (__uint_as_float(v[32 * g + i]) > tcut) ? (1u << i) : 0u;
+                    for (int j = 0; j < 8; ++j)
+                        sts_b32x4(slab + 16u * j, v[32 * g + 4 * j], v[32 * g + 4 * j + 1], v[32 * g + 4 * j + 2], v[32 * g + 4 * j + 3]);
+                    sts_u32_volatile(hdr, 0x80000000u | (uint32_t)(ridx0 + col_base + 32 * g));
+                    __threadfence_block();
+                    reds_or_u32(pend, 1u << (threadIdx.x & 31));
+                }
             }
-        }
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            uint32_t mk = mask[g];
-            while (mk) {
-                const int col = col_base + 32 * g + (__ffs((int)mk) - 1);
-                mk &= mk - 1u;
-                tc_push(q, query, (uint32_t)(ridx0 + col));
+#if TC_PROBE
+            TC_PROBE_ADD(0, 1);
+            {
+                const long long dt = clock64() - pc0;
+                TC_PROBE_ADD(1, dt);
+                
             }
+#endif
+        } else {
+            uint32_t mask[2];
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                mask[g] = 0u;
+                if (m[g] > tcut) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mask[g] |= (__uint_as_float(v[32 * g + i]) > tcut) ? (1u << i) : 0u;
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                uint32_t mk = mask[g];
+                while (mk) {
+                    const int col = col_base + 32 * g + (__ffs((int)mk) - 1);
+                    mk &= mk - 1u;
+                    tc_push(q, query, (uint32_t)(ridx0 + col));
+                }
+            }
+#if TC_PROBE
+            TC_PROBE_ADD(4, 1);
+            {
+                const long long dt = clock64() - pc0;
+                TC_PROBE_ADD(3, dt);
+                
+            }
+#endif
         }
     }
 }
@@ -378,6 +474,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
     float* th_s = reinterpret_cast<float*>(qitems + TC_QCAP);   // [256] current threshold of every query
     float* ls = th_s + TC_QUERIES;                              // [L][256] list scores
     int* li = reinterpret_cast<int*>(ls + (size_t)L * TC_QUERIES);   // [L][256] list indices
+    constexpr bool SLAB = tc_slab_on(KSTEPS);
+    // slab path: [512] slabs of 32 floats, [512] header words, [16] pending-lanes words, [256] e_q, [96] staged items
+    float* slabs = reinterpret_cast<float*>(li + (size_t)L * TC_QUERIES);
+    uint32_t* slab_hdr = reinterpret_cast<uint32_t*>(slabs + TC_EPI_WARPS * 32 * 32);
+    uint32_t* slab_pend = slab_hdr + TC_EPI_WARPS * 32;
+    float* eq_s = reinterpret_cast<float*>(slab_pend + TC_EPI_WARPS);
+    unsigned long long* stage = reinterpret_cast<unsigned long long*>(eq_s + TC_QUERIES);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -415,6 +518,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
         qctrl[0] = 0u; qctrl[1] = 0u; qctrl[2] = 0u; qctrl[3] = 0u;
     }
     for (uint32_t i = tid; i < TC_QCAP; i += TC_THREADS) qitems[i] = TC_QEMPTY;
+    if constexpr (SLAB) {
+        if (tid < TC_EPI_WARPS * 32) slab_hdr[tid] = 0u;
+        if (tid < TC_EPI_WARPS) slab_pend[tid] = 0u;
+    }
     TcQueue queue{smem_u32(qctrl), smem_u32(qitems)};
     TcEpiState st;
     st.worst = 0.f;
@@ -454,7 +561,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
         st.e_q = tp.slack_qr * qn * rmax + tp.slack_rr * rmax * rmax;
         st.valid = valid;
         st.d = p.d;
+        st.slab0 = smem_u32(slabs);
         if (half == 0) {
+            if constexpr (SLAB) eq_s[qslot] = st.e_q;
             // sweep: the final threshold of the previous chunk is a floor for this one (see FilterParams::seed_th)
             th_s[qslot] = (valid && p.seed_th && rchunk > 0)
                               ? p.cand_th[cand_th_offset(rchunk - 1, ql, p.nq_pad, p.ntail_pad, p.tail_q0)]
@@ -506,13 +615,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
             const uint32_t sbo = (tp.swap_offsets & 1) ? TC_CHUNK_BYTES : TC_ROWGROUP_BYTES;
             const uint32_t dver = (tp.swap_offsets & 2) ? 0u : 1u;
             const uint64_t desc_hi = tc_smem_desc(0, lbo, sbo, dver);
+#if TC_PROBE
+            long long probe_mwait = 0;
+#endif
             for (int it = first; it < nt; it += nw) {
                 const int buf = it & 1;
                 const int slot = it % NS, round = it / NS;
                 tc_wait(smem_u32(&bar_full[slot]), (uint32_t)round & 1u);
                 TC_MARK(it, 0);
+#if TC_PROBE
+                const long long pm0 = clock64();
+#endif
                 if (it >= 2)   // the epilogue warps have drained this buffer (tile it - 2)
                     tc_wait(smem_u32(&bar_acc_free[buf]), (uint32_t)((it >> 1) - 1) & 1u);
+#if TC_PROBE
+                probe_mwait += clock64() - pm0;
+#endif
                 TC_MARK(it, 1);
                 tc_fence_after();
                 if (elect_one()) {
@@ -532,54 +650,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
                 __syncwarp();
                 TC_MARK(it, 2);
             }
+#if TC_PROBE
+            if (lane == 0) {
+                TC_PROBE_ADD(32 + first, probe_mwait);   // [32..33] clocks an MMA warp waited for "accumulator free"
+                TC_PROBE_ADD(34, nt);                     // [34] tiles (counted by both MMA warps)
+            }
+#endif
         }
     } else if (warp == TC_SELECT_WARP) {
-        // Selection warp: pops up to 64 hits at a time, evaluates them exactly (two per lane: query row from the A
-        // tile, reference row from the image in L2) and maintains the lists and thresholds of all 256 queries.
+        // Selection warp: collects hits -- (query, reference) items pushed by the epilogue lanes during the start-up
+        // tiles, column groups spilled to slabs afterwards -- evaluates them exactly in batches of up to 64 (two per
+        // lane: query row from the A tile, reference row from the image in L2) and maintains the lists and thresholds
+        // of all 256 queries.
         const uint32_t ctrl = queue.ctrl;
         const float* img = p.tiles;
         const int d = p.d;
-        uint32_t head = 0, idle = 0;
-        for (;;) {
-            const uint32_t done = lds_u32_volatile(ctrl + 8);
-            const uint32_t tail = lds_u32_volatile(ctrl);
-            const uint32_t avail = tail - head;
-            if (avail == 0) {
-                if (done == (uint32_t)TC_EPI_WARPS) break;
-                if ((++idle & 255u) == 0u && *reinterpret_cast<volatile unsigned int*>(&g_tc_stuck[0]) != 0u) break;
-                __nanosleep(64);
-                continue;
-            }
-            // pop the written prefix of the next 64 positions, two per lane (lane l: positions l and 32 + l) -- the exact
-            // evaluation waits for one L2 round trip per batch, so a batch of 64 costs little more than one of 32.  A
-            // reserved slot may not have been written yet, and its owner may be held up by warp-mates that wait for
-            // `head` to move, so never wait for a slot here.
-            const uint32_t nres = avail < 64u ? avail : 64u;
-            unsigned long long item[2] = {TC_QEMPTY, TC_QEMPTY};
-            uint32_t addr[2];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                addr[j] = queue.items + ((head + 32u * j + lane) & (TC_QCAP - 1)) * 8u;
-                if (32u * j + (uint32_t)lane < nres) item[j] = lds_u64_volatile(addr[j]);
-            }
-            const uint32_t unw0 = __ballot_sync(0xffffffffu, (uint32_t)lane < nres && item[0] == TC_QEMPTY);
-            const uint32_t unw1 = __ballot_sync(0xffffffffu, 32u + (uint32_t)lane < nres && item[1] == TC_QEMPTY);
-            const uint32_t n = unw0 ? (uint32_t)(__ffs((int)unw0) - 1) : unw1 ? 32u + (uint32_t)(__ffs((int)unw1) - 1) : nres;
-            if (n == 0u) {
-                if ((++idle & 255u) == 0u && *reinterpret_cast<volatile unsigned int*>(&g_tc_stuck[0]) != 0u) break;
-                __nanosleep(32);
-                continue;
-            }
-            bool has[2];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                has[j] = 32u * j + (uint32_t)lane < n;
-                if (has[j]) sts_u64_volatile(addr[j], TC_QEMPTY);
-            }
-            head += n;
-            __threadfence_block();
-            __syncwarp();
-            if (lane == 0) sts_u32_volatile(ctrl + 4, head);
+        // exact evaluation and insertion of up to 64 items, lane l holding items l and 32 + l of the batch
+        auto eval_insert = [&](const unsigned long long (&item)[2], const bool (&has)[2], const uint32_t n) {
+#if TC_PROBE
+            const long long pe0 = clock64();
+#endif
             uint32_t q[2];
             int ridx[2];
             float s[2];
@@ -622,6 +712,123 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
                     __syncwarp();
                 }
             }
+#if TC_PROBE
+            if (lane == 0) {
+                TC_PROBE_ADD(5, 1);
+                TC_PROBE_ADD(6, n);
+                TC_PROBE_ADD(7, clock64() - pe0);
+            }
+#endif
+        };
+        const uint32_t stage_a = smem_u32(stage), hdr_a = smem_u32(slab_hdr), pend_a = smem_u32(slab_pend), slab_a = smem_u32(slabs);
+        const uint32_t th_a = smem_u32(th_s), eq_a = smem_u32(eq_s);
+        uint32_t head = 0, idle = 0, staged = 0;   // staged: items found in slabs, waiting in `stage` (this warp only)
+        auto flush_stage = [&]() {
+            unsigned long long item[2];
+            bool has[2];
+            __syncwarp();   // the items were staged by other lanes
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                has[j] = 32u * j + (uint32_t)lane < staged;
+                item[j] = has[j] ? lds_u64_volatile(stage_a + (32u * j + lane) * 8u) : TC_QEMPTY;
+            }
+            __syncwarp();
+            eval_insert(item, has, staged);
+            staged = 0;
+        };
+        for (;;) {
+            const uint32_t done = lds_u32_volatile(ctrl + 8);
+            const uint32_t tail = lds_u32_volatile(ctrl);
+            const uint32_t avail = tail - head;
+            bool progress = false;
+            if constexpr (SLAB) {
+                // column groups spilled by the epilogue lanes: find the passing columns (one per lane) against the
+                // query's cut of NOW, hand the slab back, stage the items
+                // Lane w looks at warp w's pending lanes and takes them off the word at once (no round trip): a lane
+                // cannot raise its bit again before its slab has been handed back below.
+                const uint32_t pend = lane < TC_EPI_WARPS ? lds_u32_volatile(pend_a + 4u * lane) : 0u;
+                if (pend != 0u) {
+                    reds_and_u32(pend_a + 4u * lane, ~pend);
+                    __threadfence_block();
+                }
+                uint32_t wmask = __ballot_sync(0xffffffffu, pend != 0u);
+                while (wmask) {
+                    const int w = __ffs((int)wmask) - 1;
+                    wmask &= wmask - 1u;
+                    uint32_t lm = __shfl_sync(0xffffffffu, pend, w);
+                    while (lm) {
+#if TC_PROBE
+                        const long long pg0 = clock64();
+#endif
+                        const int l = __ffs((int)lm) - 1;
+                        lm &= lm - 1u;
+                        const uint32_t t = (uint32_t)(w * 32 + l), qq = t & (TC_QUERIES - 1);
+                        const uint32_t hdr = lds_u32_volatile(hdr_a + 4u * t);
+                        const float x = lds_f32_volatile(slab_a + 128u * t + 4u * lane);
+                        const float cut = lds_f32_volatile(th_a + 4u * qq) - lds_f32(eq_a + 4u * qq);
+                        const uint32_t cm = __ballot_sync(0xffffffffu, x > cut);   // every lane has read its score
+                        if (lane == 0) sts_u32_volatile(hdr_a + 4u * t, 0u);      // slab back to its owner
+                        if ((cm >> lane) & 1u) {
+                            const uint32_t pos = staged + (uint32_t)__popc(cm & ((1u << lane) - 1u));
+                            sts_u64_volatile(stage_a + pos * 8u, ((unsigned long long)qq << 32) | (unsigned long long)((hdr & 0x7fffffffu) + (uint32_t)lane));
+                        }
+                        staged += (uint32_t)__popc(cm);
+#if TC_PROBE
+                        if (lane == 0) {
+                            TC_PROBE_ADD(8, 1);
+                            TC_PROBE_ADD(9, clock64() - pg0);
+                        }
+#endif
+                        if (staged >= 32u) flush_stage();
+                        progress = true;
+                    }
+                }
+            }
+            // A batch costs this warp the same few hundred issue slots whether it holds one hit or 64: wait until it is
+            // worth it (thresholds lag by the few tiles that takes, which costs next to nothing).
+            if (avail >= (done == (uint32_t)TC_EPI_WARPS ? 1u : (uint32_t)TC_SEL_MIN)) {
+                // pop the written prefix of the next 64 positions, two per lane (lane l: positions l and 32 + l) -- the exact
+                // evaluation waits for one L2 round trip per batch, so a batch of 64 costs little more than one of 32.  A
+                // reserved slot may not have been written yet, and its owner may be held up by warp-mates that wait for
+                // `head` to move, so never wait for a slot here.
+                const uint32_t nres = avail < 64u ? avail : 64u;
+                unsigned long long item[2] = {TC_QEMPTY, TC_QEMPTY};
+                uint32_t addr[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    addr[j] = queue.items + ((head + 32u * j + lane) & (TC_QCAP - 1)) * 8u;
+                    if (32u * j + (uint32_t)lane < nres) item[j] = lds_u64_volatile(addr[j]);
+                }
+                const uint32_t unw0 = __ballot_sync(0xffffffffu, (uint32_t)lane < nres && item[0] == TC_QEMPTY);
+                const uint32_t unw1 = __ballot_sync(0xffffffffu, 32u + (uint32_t)lane < nres && item[1] == TC_QEMPTY);
+                const uint32_t n = unw0 ? (uint32_t)(__ffs((int)unw0) - 1) : unw1 ? 32u + (uint32_t)(__ffs((int)unw1) - 1) : nres;
+                if (n != 0u) {
+                    bool has[2];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        has[j] = 32u * j + (uint32_t)lane < n;
+                        if (has[j]) sts_u64_volatile(addr[j], TC_QEMPTY);
+                    }
+                    head += n;
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) sts_u32_volatile(ctrl + 4, head);
+                    eval_insert(item, has, n);
+                    progress = true;
+                }
+            }
+            if (progress) {
+                idle = 0;
+                continue;
+            }
+            ++idle;
+            if (staged != 0u && (idle >= 8u || done == (uint32_t)TC_EPI_WARPS)) {   // nothing else to do: the leftovers
+                flush_stage();
+                continue;
+            }
+            if (done == (uint32_t)TC_EPI_WARPS && avail == 0u && staged == 0u) break;   // `done` was read before the queue and the slabs
+            if ((idle & 255u) == 0u && *reinterpret_cast<volatile unsigned int*>(&g_tc_stuck[0]) != 0u) break;
+            __nanosleep(avail == 0u ? 64 : 256);
         }
     } else {
         const int mb = (warp >> 2) & 1, quad = warp & 3;
@@ -630,6 +837,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
         const uint32_t acc_full0 = smem_u32(&bar_acc_full[0]), acc_free0 = smem_u32(&bar_acc_free[0]);
         const uint32_t slot_bar0 = smem_u32(&bar_free[0]), slot_bar_end = slot_bar0 + (uint32_t)NS * 8u;
         const uint32_t ring0 = smem_u32(ring);
+        // a unit that starts from the thresholds of the chunk before it (sweep) has no start-up phase
+        const int slab_t0 = (p.seed_th && rchunk > 0) ? 0 : TC_SLAB_T0 * L;   // even
         // invalid queries never pass: th - e_q is NaN (th starts at -inf) or +inf
         const float e_q = (st.valid && MODE != 5) ? st.e_q : -CUDART_INF_F;   // MODE 5: nothing ever passes
 
@@ -673,10 +882,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
         // thread: one barrier wait, one TMEM load of this thread's 64 columns, two arrivals (accumulator buffer back
         // to the MMA issuer, ring slot back to the producer), 35 FMNMX and one compare.
         uint32_t parity = 0u, slot_bar = slot_bar0;
+#if TC_PROBE
+        long long probe_wait = 0;   // clocks this warp waited for "accumulator full"
+#endif
         int ridx0 = t0 * TC_TILE_REFS;
-        auto one_tile = [&](const int buf, const int it) {
+        auto one_tile = [&](const int buf, const int it, auto use_slab_c) {
+            constexpr bool US = decltype(use_slab_c)::value;
+#if TC_PROBE
+            const long long pw0 = clock64();
+#endif
             tc_wait(acc_full0 + 8u * buf, parity);
             __syncwarp();   // lanes may leave the wait at different times; the TMEM load is warp-collective
+#if TC_PROBE
+            probe_wait += clock64() - pw0;
+#endif
             tc_fence_after();
             if (quad == 0 && half == 0) TC_MARK(it, 5 + 3 * mb);
             const uint32_t taddr = tlane + 256u * buf;
@@ -696,11 +915,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
                     st.full_bar = smem_u32(&bar_full[slot]);
                     st.full_parity = (uint32_t)(it / NS) & 1u;
                     st.dump_row = (tp.dump && blockIdx.x == 0 && it == 0) ? tp.dump + (size_t)qslot * TC_TILE_REFS : nullptr;
-                    tc_process_tile<KSTEPS, CHECK>(v, ring0 + (uint32_t)slot * TILE_BYTES, col_base, ridx0, tcut, (uint32_t)qslot, queue, st);
+                    tc_process_tile<KSTEPS, CHECK, US>(v, ring0 + (uint32_t)slot * TILE_BYTES, col_base, ridx0, tcut, (uint32_t)qslot, queue, st);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(slot_bar);
                 } else {
-                    tc_process_tile<KSTEPS, CHECK>(v, 0u, col_base, ridx0, tcut, (uint32_t)qslot, queue, st);
+                    tc_process_tile<KSTEPS, CHECK, US>(v, 0u, col_base, ridx0, tcut, (uint32_t)qslot, queue, st);
                 }
             } else {
                 if constexpr (MODE == 4) {   // the loads alone
@@ -721,12 +940,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
             if (slot_bar == slot_bar_end) slot_bar = slot_bar0;
             ridx0 += TC_TILE_REFS;
         };
+        // two copies of the loop: the start-up tiles with the column-precise hit path, the rest with the slab path
+        int it = 0;
+        const int nt0 = SLAB ? (nt < slab_t0 ? nt : slab_t0) : nt;   // slab_t0 is even
 #pragma unroll 1
-        for (int it = 0; it < nt; it += 2) {
-            one_tile(0, it);
-            if (it + 1 < nt) one_tile(1, it + 1);
+        for (; it < nt0; it += 2) {
+            one_tile(0, it, std::false_type{});
+            if (it + 1 < nt) one_tile(1, it + 1, std::false_type{});
             parity ^= 1u;
         }
+        if constexpr (SLAB) {
+#pragma unroll 1
+            for (; it < nt; it += 2) {
+                one_tile(0, it, std::true_type{});
+                if (it + 1 < nt) one_tile(1, it + 1, std::true_type{});
+                parity ^= 1u;
+            }
+        }
+#if TC_PROBE
+        if (lane == 0) TC_PROBE_ADD(16 + warp, probe_wait);   // [16..31]
+#endif
         // every hit of this warp is in the queue: tell the selection warp
         __threadfence_block();
         __syncwarp();
@@ -757,7 +990,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
 
 size_t tc_fixed_smem(int K, int list_len) {
     return (size_t)2 * K * TC_QBLK * 4 + (size_t)(2 * 8 + 8) * sizeof(uint64_t) + 16 + 16 + (size_t)TC_QCAP * 8 +
-           (size_t)TC_QUERIES * 4 + (size_t)list_len * TC_QUERIES * (sizeof(float) + sizeof(int));
+           (size_t)TC_QUERIES * 4 + (size_t)list_len * TC_QUERIES * (sizeof(float) + sizeof(int)) +
+           (tc_slab_on(K / 8) ? TC_SLAB_BYTES : 0);
 }
 
 template <int KSTEPS, int MODE>
@@ -819,6 +1053,14 @@ __global__ void __launch_bounds__(128) tc_image_kernel(const double* __restrict_
 
 }  // namespace
 
+}  // namespace mce
+// development: copies the TC_PROBE counters of the current device to out[64] and clears them
+extern "C" int mce_tc_probe(unsigned long long* out) {
+    if (cudaMemcpyFromSymbol(out, mce::g_tc_probe, 64 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+    const unsigned long long zero[64] = {};
+    return cudaMemcpyToSymbol(mce::g_tc_probe, zero, sizeof(zero)) == cudaSuccess ? 0 : -1;
+}
+namespace mce {
 // Give-up record of the barrier waits (tcgen05.cuh): copies {flag, a, b, block} to `out` and clears it on the device.
 int tc_read_stuck(unsigned int (&out)[4], cudaStream_t st) {
     if (cudaMemcpyFromSymbolAsync(out, g_tc_stuck, sizeof(out), 0, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
