@@ -52,9 +52,9 @@ FP32_PEAK_THEORETICAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.4: SMs x la
 # dram__bytes_read.sum + dram__bytes_write.sum of one K2 launch from the ncu --set full capture of this command
 # (profiles/r01_filter_ncu_raw_final.csv: 148.7 MB read + 31.2 MB written; algorithmic: 44 MB tiles + 80 MB
 # queries + ~24 MB candidate lists -- the reference set is streamed from L2, not from HBM)
-# tcgen05 engine (profiles/r02_tc_filter_ncu_raw_cfg2.csv): 670.4 MB read + 32.0 MB written; algorithmic: 64 MB image +
+# tcgen05 engine (profiles/r02_tc_filter_ncu_raw_cfg2_final.csv): 738.5 MB read + 43.5 MB written; algorithmic: 64 MB image +
 # 80 MB queries + ~25 MB candidate lists -- the image is re-read from HBM when it falls out of L2 between query blocks
-NCU_DRAM_BYTES_PER_LAUNCH = {('cfg2', 1, False): 179.9e6, ('cfg2', 1, True): 702.3e6}   # (workload, gpus, tcgen05 engine?)
+NCU_DRAM_BYTES_PER_LAUNCH = {('cfg2', 1, False): 179.9e6, ('cfg2', 1, True): 781.9e6}   # (workload, gpus, tcgen05 engine?)
 METRIC = 'knn_pair_dists_per_s'
 UNIT = 'pair-dists/s'
 

@@ -483,7 +483,7 @@ int enqueue_problem(mce_ctx* c, const Run& r, Pending& pd) {
             // an explicit FFMA tiling option (tests, tuning runs) keeps the FFMA filter
             const bool ffma_tuned = c->opt_tq > 0 || c->opt_tr > 0 || c->opt_packed >= 0 || c->opt_sync >= 0;
             const double pairs = (double)nq * (double)n_ref;
-            const double min_pairs = c->opt_tc_min_mpairs > 0 ? 1e6 * c->opt_tc_min_mpairs : 3e8;
+            const double min_pairs = c->opt_tc_min_mpairs > 0 ? 1e6 * c->opt_tc_min_mpairs : (d <= 6 ? 2e8 : 3e8);   // ndim <= 6: K = 8, one MMA per tile
             use_tc = fits && !ffma_tuned && d >= 4 && pairs >= min_pairs;
         }
     }

@@ -39,6 +39,12 @@
 #ifndef TC_SLAB_T0
 #define TC_SLAB_T0 300      // x list length = tiles of a unit that keep the column-precise hit path: about 350 x L / t hits per
 #endif                      // tile reach the selection warp, which handles ~2 slab events per tile time (profiles/r02_tc_ab_*.jsonl)
+#ifndef TC_BOOT_TILES
+#define TC_BOOT_TILES 128   // tiles of a (long) unit that are first looked at for the threshold only (even; 0 = first tile only)
+#endif
+#ifndef TC_BOOT_DIV
+#define TC_BOOT_DIV 12
+#endif
 #ifndef TC_SEL_MIN
 #define TC_SEL_MIN 32       // the selection warp evaluates a batch when at least this many hits are waiting
 #endif
@@ -128,6 +134,10 @@ __device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
 constexpr uint32_t TC_LIST_STRIDE = TC_QUERIES * 4;   // bytes between consecutive entries of one query's list
 constexpr int TC_LMAX = MCE_TC_LIST_MAX;              // longest list: KCAP neighbours + margin
 constexpr int TC_BOOT = 9;                            // bootstrap network: the 9 largest coarse scores of a unit's first tile
+#ifndef TC_BOOT_DEEP_N
+#define TC_BOOT_DEEP_N 13
+#endif
+constexpr int TC_BOOT_DEEP = TC_BOOT_DEEP_N;                      // multi-tile bootstrap of long lists (kmax 8 .. 10): 13 largest group maxima
 constexpr uint32_t TC_QCAP = 512;                     // hit-queue slots (power of two)
 constexpr unsigned long long TC_QEMPTY = 0xFFFFFFFFFFFFFFFFull;
 // TC_PROBE builds: [0] hit-path entries (lanes), [1] clocks inside, [2] entries that found their slab taken, [3] clocks of
@@ -342,8 +352,13 @@ __device__ __forceinline__ void tc_process_tile(const uint32_t (&v)[TC_HALF_COLS
         }
     }
     float m[2];
+#if defined(TC_HALF_TREE)   // timing experiment: half of the max tree (results are garbage)
+    m[0] = max32(&v[0]);
+    m[1] = fmaxf(__uint_as_float(v[32]), __uint_as_float(v[63]));
+#else
 #pragma unroll
     for (int g = 0; g < 2; ++g) m[g] = max32(&v[32 * g]);
+#endif
     if (fmaxf(m[0], m[1]) > tcut) {
         // The pipeline has no slack: whatever this warp spends here, all twenty wait for two tiles later (measured: the
         // cost of a hit is the LATENCY of this path, not its instruction count and not the selection warp's time).
@@ -426,10 +441,11 @@ __device__ __forceinline__ void tc_process_tile(const uint32_t (&v)[TC_HALF_COLS
     }
 }
 
-// Descending insertion network: keeps the TC_BOOT largest values seen.
-__device__ __forceinline__ void tc_boot_insert(float (&t)[TC_BOOT], float x) {
+// Descending insertion network: keeps the NB largest values seen.
+template <int NB>
+__device__ __forceinline__ void tc_boot_insert(float (&t)[NB], float x) {
 #pragma unroll
-    for (int i = 0; i < TC_BOOT; ++i) {
+    for (int i = 0; i < NB; ++i) {
         const float hi = fmaxf(t[i], x);
         x = fminf(t[i], x);
         t[i] = hi;
@@ -502,6 +518,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
     }
     const int nt = t1 - t0;
     const long long nq = p.q_end - p.q_begin;
+    // Long units look at their first `boot` tiles twice: once for the threshold alone (the epilogue keeps the largest
+    // group maxima, nothing is evaluated exactly), then again as part of the normal pass, which starts from a
+    // threshold that has seen boot x 128 references.  Two thirds of the hits of a unit used to fall into these tiles,
+    // where the selection warp -- not the tensor core -- set the pace.
+    int boot = 0;   // even; a twelfth of the unit at most, shorter units keep the first-tile bootstrap of the epilogue
+    if (MODE == 0 && TC_BOOT_TILES > 0 && L + 1 <= TC_BOOT_DEEP && !(p.seed_th && rchunk > 0)) {
+        boot = (nt / TC_BOOT_DIV) & ~1;
+        boot = boot > TC_BOOT_TILES ? TC_BOOT_TILES : (boot < 4 ? 0 : boot);
+    }
+    const int ntv = nt + boot;   // tiles in the order they are loaded and multiplied: 0 .. boot-1, then 0 .. nt-1
 
     // ---- set-up ----------------------------------------------------------------------------------
     if (warp == TC_MMA_WARP) tmem_alloc(smem_u32(tmem_slot), TC_TMEM_COLS);
@@ -585,7 +611,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
         if (elect_one()) {
             const unsigned char* gt = reinterpret_cast<const unsigned char*>(p.tiles) + (size_t)t0 * TILE_BYTES;
             int slot = 0, round = 0;
-            for (int n = 0; n < nt; ++n) {
+            for (int n = 0; n < ntv; ++n) {
                 if (round > 0) {
                     const uint32_t fb = smem_u32(&bar_free[slot]);
                     tc_wait_relaxed(fb, (uint32_t)(round - 1) & 1u);
@@ -595,7 +621,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
                 }
                 const uint32_t bar = smem_u32(&bar_full[slot]);
                 mbar_arrive_expect_tx(bar, TILE_BYTES);
-                tma_bulk_g2s(smem_u32(ring) + (uint32_t)slot * TILE_BYTES, gt + (size_t)n * TILE_BYTES, TILE_BYTES, bar);
+                tma_bulk_g2s(smem_u32(ring) + (uint32_t)slot * TILE_BYTES, gt + (size_t)(n < boot ? n : n - boot) * TILE_BYTES, TILE_BYTES, bar);
                 if (++slot == NS) {
                     slot = 0;
                     ++round;
@@ -618,7 +644,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
 #if TC_PROBE
             long long probe_mwait = 0;
 #endif
-            for (int it = first; it < nt; it += nw) {
+            for (int it = first; it < ntv; it += nw) {
                 const int buf = it & 1;
                 const int slot = it % NS, round = it / NS;
                 tc_wait(smem_u32(&bar_full[slot]), (uint32_t)round & 1u);
@@ -842,11 +868,66 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
         // invalid queries never pass: th - e_q is NaN (th starts at -inf) or +inf
         const float e_q = (st.valid && MODE != 5) ? st.e_q : -CUDART_INF_F;   // MODE 5: nothing ever passes
 
-        if (MODE <= 2 && nt > 0 && L + 1 <= TC_BOOT) {
-            // Bootstrap: the (L+1)-th largest coarse score c among this thread's columns of the unit's first tile.
-            // At least L references other than the query itself have an exact score >= c - e, so the threshold can
-            // start from there instead of -inf (the larger of the two halves wins): the first tile then yields a
-            // handful of hits per query instead of 128.  The tile is processed again by the loop below.
+        uint32_t parity = 0u, slot_bar = slot_bar0;
+        // The threshold can start from c - e, c the (L+1)-th largest coarse score seen: at least L references other than the
+        // query itself have an exact score >= c - e (the larger of the two column halves wins).
+        auto raise_threshold = [&](const auto& t) {
+            constexpr int NB = (int)(sizeof(t) / sizeof(float));
+            float c0 = -CUDART_INF_F;
+#pragma unroll
+            for (int i = 0; i < NB; ++i) c0 = (i == L) ? t[i] : c0;
+            if (st.valid && c0 > -CUDART_INF_F) {
+                const float th0 = c0 - st.e_q * 1.001f - 1e-30f;
+                // float maximum through compare-and-swap on the bit pattern (twice per query and unit)
+                uint32_t old = lds_u32_volatile(st.th_addr);
+                while (th0 > __uint_as_float(old)) {
+                    uint32_t seen;
+                    asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(seen) : "r"(st.th_addr), "r"(old), "r"(__float_as_uint(th0)) : "memory");
+                    if (seen == old) break;
+                    old = seen;
+                }
+            }
+            __threadfence_block();
+        };
+        // Bootstrap of a long unit: the maxima of this thread's two 32-column groups of each of the first `boot` tiles
+        // (distinct references) go through the insertion network; no hit path, nothing for the selection warp.
+        auto run_boot = [&](auto depth_c) {
+            constexpr int NB = decltype(depth_c)::value;
+            float t[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) t[i] = -CUDART_INF_F;
+            auto boot_tile = [&](const int buf) {
+                tc_wait(acc_full0 + 8u * buf, parity);
+                __syncwarp();
+                tc_fence_after();
+                uint32_t v[TC_HALF_COLS];
+                tmem_ld64_wait(tlane + 256u * buf, v);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(acc_free0 + 8u * buf);
+                    mbar_arrive(slot_bar);
+                }
+                tc_boot_insert(t, max32(&v[0]));
+                tc_boot_insert(t, max32(&v[32]));
+                slot_bar += 8u;
+                if (slot_bar == slot_bar_end) slot_bar = slot_bar0;
+            };
+#pragma unroll 1
+            for (int j = 0; j < boot; j += 2) {
+                boot_tile(0);
+                boot_tile(1);
+                parity ^= 1u;
+            }
+            raise_threshold(t);
+        };
+        if (boot > 0) {
+            if (L + 1 <= TC_BOOT) run_boot(std::integral_constant<int, TC_BOOT>{});
+            else run_boot(std::integral_constant<int, TC_BOOT_DEEP>{});
+        } else if (MODE <= 2 && nt > 0 && L + 1 <= TC_BOOT) {
+            // Bootstrap of a short unit: the (L+1)-th largest coarse score among this thread's columns of the first tile,
+            // so that the first tile yields a handful of hits per query instead of 128.  The tile is processed again
+            // by the loop below.
             tc_wait(acc_full0, 0u);
             __syncwarp();
             tc_fence_after();
@@ -861,27 +942,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
 #pragma unroll
                 for (int i = 0; i < 32; ++i) tc_boot_insert(t, __uint_as_float(w[i]));
             }
-            float c0 = -CUDART_INF_F;
-#pragma unroll
-            for (int i = 0; i < TC_BOOT; ++i) c0 = (i == L) ? t[i] : c0;
-            if (st.valid && c0 > -CUDART_INF_F) {
-                const float th0 = c0 - st.e_q * 1.001f - 1e-30f;
-                // float maximum through compare-and-swap on the bit pattern (twice per query and unit)
-                uint32_t old = lds_u32_volatile(st.th_addr);
-                while (th0 > __uint_as_float(old)) {
-                    uint32_t seen;
-                    asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(seen) : "r"(st.th_addr), "r"(old), "r"(__float_as_uint(th0)) : "memory");
-                    if (seen == old) break;
-                    old = seen;
-                }
-            }
-            __threadfence_block();
+            raise_threshold(t);
         }
 
         // Tile loop, unrolled over the two accumulator buffers so that every address is loop-invariant.  Per tile and
         // thread: one barrier wait, one TMEM load of this thread's 64 columns, two arrivals (accumulator buffer back
         // to the MMA issuer, ring slot back to the producer), 35 FMNMX and one compare.
-        uint32_t parity = 0u, slot_bar = slot_bar0;
 #if TC_PROBE
         long long probe_wait = 0;   // clocks this warp waited for "accumulator full"
 #endif

@@ -80,6 +80,24 @@ def test_tc_matches_ffma_engine(tc, d):
     np.testing.assert_allclose(r1['logE'], r0['logE'], rtol=0, atol=1e-12)
 
 
+@pytest.mark.parametrize('n,d,k', [(400000, 10, 2), (300000, 20, 9), (420000, 6, 5)])
+def test_tc_long_units_bootstrap_and_slabs(tc, n, d, k):
+    """Units long enough for the multi-tile threshold bootstrap (its 9- and 13-deep networks) and for the slab hit path
+    that follows the start-up tiles (whole-range units: no reference split): neighbours equal the FFMA engine's bit for
+    bit."""
+    chain, _ = gaussian_chain(n, d, seed=23)
+    x = np.ascontiguousarray(chain[:, 2:])
+    tc.set_option('ref_chunks', 1)
+    d1, i1, st = tc.knn(x, k)
+    assert st['filter_mode'] == 16
+    tc.set_option('filter_engine', 0)
+    tc.set_option('ref_chunks', -1)
+    d0, i0, st0 = tc.knn(x, k)
+    assert st0['filter_mode'] != 16
+    np.testing.assert_array_equal(i1, i0)
+    np.testing.assert_array_equal(d1, d0)
+
+
 def test_tc_duplicates_and_padding(tc):
     """Duplicate rows (distance 0 ties ordered by index) and a reference count that is not a tile multiple."""
     rng = np.random.default_rng(5)
