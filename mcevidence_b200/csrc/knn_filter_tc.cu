@@ -45,6 +45,9 @@
 #ifndef TC_BOOT_DIV
 #define TC_BOOT_DIV 12
 #endif
+#ifndef TC_SPLIT_LD
+#define TC_SPLIT_LD 0       // 1: the 64 columns are loaded as two 32-column halves, the max of the first taken while the second arrives
+#endif
 #ifndef TC_SEL_MIN
 #define TC_SEL_MIN 32       // the selection warp evaluates a batch when at least this many hits are waiting
 #endif
@@ -968,7 +971,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
             if constexpr (MODE <= 2 || MODE == 5) {
                 const float tcut = lds_f32_volatile(st.th_addr) - e_q;
                 uint32_t v[TC_HALF_COLS];
+#if TC_SPLIT_LD
+                {
+                    uint32_t(&va)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+                    uint32_t(&vb)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+                    tmem_ld32(taddr, va);
+                    tmem_wait_ld(va);
+                    tmem_ld32(taddr + 32u, vb);
+                    const float m0 = max32(&v[0]);
+                    asm volatile("" ::"f"(m0));   // taken while the second half is in flight
+                    tmem_wait_ld(vb);
+                }
+#else
                 tmem_ld64_wait(taddr, v);
+#endif
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
