@@ -143,10 +143,10 @@ int  mce_ctx_set_stream(mce_ctx *ctx, void *cuda_stream);
    problems of mce_evidence_batch.  "batch_stage" (default 1): mce_evidence_batch packs the used columns of the host arrays
    into a pinned arena on a few host threads so that the uploads overlap the kernels; 0 = copy from the caller's
    (pageable) arrays directly.  "tc_min_mpairs": the automatic engine choice takes the tcgen05 filter from
-   this many million pairs on (0 = the measured default, 300).  "sweep_seed" (default 1): mce_evidence_sweep launches the filter once per batch
+   this many million pairs on (0 = the measured default: 200 for ndim <= 6, 300 above).  "sweep_seed" (default 1): mce_evidence_sweep launches the filter once per batch
    boundary and seeds every range with the thresholds of the one before; 0 = one launch with restarted lists.
-   "filter_engine": 2 = chosen per problem (default: the tcgen05 filter for ndim >= 4 and at least ~3e8 pairs, 3e8
-   from ndim 10 on -- where it was measured faster on B200 -- otherwise the FP32 FFMA filter), 0 = FFMA filter,
+   "filter_engine": 2 = chosen per problem (default: the tcgen05 filter for ndim >= 4 and at least ~3e8 pairs, 2e8
+   up to ndim 6 -- where it was measured faster on B200 -- otherwise the FP32 FFMA filter), 0 = FFMA filter,
    1 = tcgen05 tensor-core filter (TF32 coarse scores in TMEM, exact FP32 evaluation of the columns that pass; same
    candidates contract, stats.filter_mode reports 16); the environment variable MCE_FILTER_ENGINE=0/1/2 sets the
    initial value of every new context.

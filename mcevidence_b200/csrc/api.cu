@@ -128,7 +128,7 @@ struct mce_ctx {
     int opt_tq = -1, opt_tr = -1, opt_packed = -1, opt_chunks = -1, opt_margin = -1, opt_sync = -1, opt_tail = -1;
     // engine of the filter: 0 = FFMA filter, 1 = tcgen05, 2 = chosen per problem (default); check = also evaluate every
     // pair exactly and record the worst |coarse - exact| / e; slack = percent of the default error allowance
-    int opt_engine = 2, opt_tc_check = 0, opt_tc_swap = 0, opt_tc_slack = 100, opt_tc_stages = -1, opt_tc_perf = 0, opt_tc_timeline = 0, opt_tc_mma_warps = 2, opt_tc_variant = 0;
+    int opt_engine = 2, opt_tc_check = 0, opt_tc_swap = 0, opt_tc_slack = 100, opt_tc_stages = -1, opt_tc_perf = 0, opt_tc_timeline = 0, opt_tc_mma_warps = 2;
     double dbg_tc_ratio = 0.0, dbg_tc_pairs = 0.0;
     std::vector<float> dbg_tc_dump;   // tc_check: coarse scores of unit 0, tile 0 ([256 queries][128 references])
     DevBuf xq, xr, logl, w, yr, yq, tiles, tc_tiles, tc_debug, tc_dump, cand_idx, cand_th, dknn, idx, flagged, covpart, redpart, scal,
@@ -706,7 +706,6 @@ int enqueue_problem(mce_ctx* c, const Run& r, Pending& pd) {
             tp.check = c->opt_tc_check;
             tp.perf_mode = c->opt_tc_perf;
             tp.mma_warps = c->opt_tc_mma_warps;
-            tp.variant = c->opt_tc_variant;
             for (int cb = 0; cb < nlaunch; ++cb) {
                 tp.f.chunk_base = cb;
                 if (launch_tc_filter(tp, st, &launches) != 0)
@@ -1083,7 +1082,6 @@ int mce_ctx_set_option(mce_ctx* c, const char* name, int value) {
     else if (!strcmp(name, "tc_stages")) c->opt_tc_stages = value;
     else if (!strcmp(name, "tc_timeline")) c->opt_tc_timeline = value != 0;
     else if (!strcmp(name, "tc_mma_warps")) c->opt_tc_mma_warps = value == 1 ? 1 : 2;
-    else if (!strcmp(name, "tc_variant")) c->opt_tc_variant = value;
     else if (!strcmp(name, "tc_perf_mode")) c->opt_tc_perf = (value >= 1 && value <= 3) ? value : 0;
     else if (!strcmp(name, "tc_slack_percent")) {
         if (value < 1) return fail(MCE_ERR_ARG, "tc_slack_percent must be positive");
@@ -1177,7 +1175,7 @@ int mce_evidence_batch(mce_ctx* c, int n, const mce_problem* problems, mce_resul
         lane->opt_tq = c->opt_tq; lane->opt_tr = c->opt_tr; lane->opt_packed = c->opt_packed; lane->opt_chunks = c->opt_chunks;
         lane->opt_margin = c->opt_margin; lane->opt_sync = c->opt_sync; lane->opt_tail = c->opt_tail;
         lane->opt_engine = c->opt_engine; lane->opt_tc_slack = c->opt_tc_slack; lane->opt_tc_stages = c->opt_tc_stages;
-        lane->opt_tc_mma_warps = c->opt_tc_mma_warps; lane->opt_tc_variant = c->opt_tc_variant;
+        lane->opt_tc_mma_warps = c->opt_tc_mma_warps;
         lane->opt_tc_min_mpairs = c->opt_tc_min_mpairs;
         lane->share = nl;
     }

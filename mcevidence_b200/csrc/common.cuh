@@ -138,7 +138,6 @@ struct TcFilterParams {
     int swap_offsets;                 // debug bits: 1 = exchange the leading/stride byte offsets of the descriptors, 2 = version field 0
     int check;                        // 1: evaluate every pair exactly as well and record the worst ratio in debug[]
     int mma_warps;                    // 1 or 2 warps issuing the MMAs (2: even / odd tiles)
-    int variant;                      // bit 0: stagger the two column-half warps of a pair (load / compute in antiphase)
     int perf_mode;                    // timing experiments only (results are garbage): 1 = epilogue skips the TMEM loads
                                       // (MMA + TMA pipeline alone), 2 = loads without the threshold test
 };

@@ -1,5 +1,5 @@
 // K2-TC: tensor-core engine of the neighbour filter (tcgen05 + TMEM + TMA, sm_100a).  Validated on B200 (bit-identical
-// neighbours and logE: tests/test_gpu_tc.py and the whole GPU suite) and chosen automatically for ndim >= 4 from ~3e8
+// neighbours and logE: tests/test_gpu_tc.py and the whole GPU suite) and chosen automatically for ndim >= 4 from ~3e8 (ndim <= 6: 2e8)
 // pairs on ("filter_engine" = 2, the default; 1 forces it, 0 forces the FFMA filter of knn_filter.cuh).
 //
 // Replaces the same reference step as the FFMA filter, the neighbour search of
@@ -26,6 +26,15 @@
 // evaluated exactly: the FP32 FMA chain of the FFMA filter, read from the very same operand tiles,
 // and inserted if they beat th.  Hence no reference whose FP32 score exceeds the final threshold
 // is ever dropped, which is the invariant K3's verification relies on.
+//
+// Hits.  A query meets ~L (1 + ln T) references that beat its running threshold over T tiles, most of them early, and
+// what a hit costs is the latency of its path in the owning warp (the sixteen epilogue warps run in lockstep).  Hence
+//   (1) long units first look at their first min(128, nt / 12) tiles for the threshold alone (group maxima through an
+//       insertion network, nothing evaluated exactly), then scan all tiles from a warm threshold;
+//   (2) during the first 300 L tiles a hit lane finds its passing columns itself and pushes (query, reference) items
+//       into a shared-memory queue; afterwards it only spills the 32 coarse scores of the group into its slab (stores
+//       and one reduction) and the selection warp finds the columns.
+// DESIGN.md (K2-TC) has the measurements behind both, and those of the variants that lost.
 #include "common.cuh"
 #include "knn_filter.cuh"
 #include "tcgen05.cuh"
