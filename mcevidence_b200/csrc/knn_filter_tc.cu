@@ -57,6 +57,9 @@
 #ifndef TC_SPLIT_LD
 #define TC_SPLIT_LD 0       // 1: the 64 columns are loaded as two 32-column halves, the max of the first taken while the second arrives
 #endif
+#ifndef TC_FENCE_ACQREL
+#define TC_FENCE_ACQREL 0   // 1: fence.acq_rel.cta instead of __threadfence_block() (MEMBAR.SC.CTA) on the slab path
+#endif
 #ifndef TC_SEL_MIN
 #define TC_SEL_MIN 32       // the selection warp evaluates a batch when at least this many hits are waiting
 #endif
@@ -410,7 +413,11 @@ __device__ __forceinline__ void tc_process_tile(const uint32_t (&v)[TC_HALF_COLS
                     for (int j = 0; j < 8; ++j)
                         sts_b32x4(slab + 16u * j, v[32 * g + 4 * j], v[32 * g + 4 * j + 1], v[32 * g + 4 * j + 2], v[32 * g + 4 * j + 3]);
                     sts_u32_volatile(hdr, 0x80000000u | (uint32_t)(ridx0 + col_base + 32 * g));
+#if TC_FENCE_ACQREL
+                    asm volatile("fence.acq_rel.cta;" ::: "memory");
+#else
                     __threadfence_block();
+#endif
                     reds_or_u32(pend, 1u << (threadIdx.x & 31));
                 }
             }
@@ -534,9 +541,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
     // group maxima, nothing is evaluated exactly), then again as part of the normal pass, which starts from a
     // threshold that has seen boot x 128 references.  Two thirds of the hits of a unit used to fall into these tiles,
     // where the selection warp -- not the tensor core -- set the pace.
-    int boot = 0;   // even; a twelfth of the unit at most, shorter units keep the first-tile bootstrap of the epilogue
+    int boot = 0;   // even; a twelfth of the unit (a sixth below 128 tiles), under 4 tiles the first-tile bootstrap of the epilogue
     if (MODE == 0 && TC_BOOT_TILES > 0 && L + 1 <= TC_BOOT_DEEP && !(p.seed_th && rchunk > 0)) {
-        boot = (nt / TC_BOOT_DIV) & ~1;
+        boot = (nt / (nt < 128 ? TC_BOOT_DIV / 2 : TC_BOOT_DIV)) & ~1;   // short units (small chains, split references): a sixth
         boot = boot > TC_BOOT_TILES ? TC_BOOT_TILES : (boot < 4 ? 0 : boot);
     }
     const int ntv = nt + boot;   // tiles in the order they are loaded and multiplied: 0 .. boot-1, then 0 .. nt-1
