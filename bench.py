@@ -536,7 +536,11 @@ def main():
     if args.filter_engine is not None:
         ctx.set_option('filter_engine', {'ffma': 0, 'tc': 1, 'auto': 2}[args.filter_engine])
 
-    wl = make_workload(args.workload) if rank == 0 else None
+    # e2e at N > 1: every rank holds the (same, seeded) chain on its host, as the ranks of the reference's MPI driver each
+    # read their files; a rank uploads its own block of rows and the blocks are all-gathered (dist.evidence_sharded,
+    # host_on_every_rank).  The resident leg still starts from rank 0's copy, broadcast once before the timed region.
+    every_rank_host = world > 1 and not args.no_e2e
+    wl = make_workload(args.workload) if (rank == 0 or every_rank_host) else None
     meta = [None]
     if rank == 0:
         meta = [{k: wl[k] for k in ('d', 'kmax', 'cross', 'desc', 'lnZ')}]
@@ -554,7 +558,7 @@ def main():
         t.numpy()[...] = a
         return t
     host = {}
-    if rank == 0:
+    if rank == 0 or every_rank_host:
         host = {'samples': pinned(np.ascontiguousarray(wl['s1'][:, :wl['d']])), 'logl': pinned(wl['logl']), 'weights': pinned(wl['w'])}
         if cross:
             host['ref'] = pinned(wl['s2'])
@@ -580,10 +584,9 @@ def main():
         if world == 1:
             return ctx.evidence(host['samples'].numpy(), host['logl'].numpy(), host['weights'].numpy(), kmax,
                                 ref=host['ref'].numpy() if cross else None, ndim=d, log_sum_w=math.log(sum_w))
-        if rank == 0:
-            return evidence_sharded(host['samples'].numpy(), host['logl'].numpy(), host['weights'].numpy(), kmax,
-                                    ref=host['ref'].numpy() if cross else None, ndim=d, sum_w=sum_w, ctx=ctx, device=device)
-        return evidence_sharded(None, None, None, kmax, ctx=ctx, device=device)
+        return evidence_sharded(host['samples'].numpy(), host['logl'].numpy(), host['weights'].numpy(), kmax,
+                                ref=host['ref'].numpy() if cross else None, ndim=d, sum_w=sum_w, ctx=ctx, device=device,
+                                host_on_every_rank=True)
 
     def barrier():
         if world > 1:
@@ -683,6 +686,8 @@ def main():
                 'dtype': 'f32 filter, f64 re-rank/reduce', 'data': 'synthetic',
                 'config': config_for(args.workload, world),
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                        'upload': ('one H2D copy of the pinned arrays' if world == 1 else
+                                   'each rank copies its own 1/%d of the rows from its pinned host arrays, NCCL all-gather' % world),
                         's_per_logE': None if args.no_e2e else te / args.steps},
                 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline,
                 's_per_logE': t_ms * 1e-3 / args.steps, 'logE': [float(x) for x in loge],

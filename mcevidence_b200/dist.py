@@ -56,11 +56,14 @@ def allreduce_partials(partials, group=None, device=None):
 
 
 def evidence_sharded(samples, logl, weights, kmax, ref=None, ndim=None, priorvolume=1.0, sum_w=None,
-                     group=None, device=None, compute=None, ctx=None, resident=None):
+                     group=None, device=None, compute=None, ctx=None, resident=None, host_on_every_rank=False):
     """Log-evidence with query rows sharded over the ranks of ``group``.
 
     Rank 0 passes the host arrays (other ranks may pass ``None``); every rank returns the same
-    ``dict(logE, var_logE, stats)``.  ``compute(arrays, q_range) -> (partials, log_jacobian, stats)``
+    ``dict(logE, var_logE, stats)``.  ``host_on_every_rank``: EVERY rank passes the same host arrays (each process read
+    the chain files itself, as the ranks of the reference's MPI driver do, ``planck_mcevidence.py:149-160``); a rank then
+    uploads only its own block of rows over its own PCIe link and the blocks are all-gathered over NVLink instead of
+    one upload on rank 0 followed by a broadcast.  ``compute(arrays, q_range) -> (partials, log_jacobian, stats)``
     replaces the CUDA call in the CPU tests of the sharding/combination logic.  ``resident``: a dict
     of CUDA tensors already broadcast (``samples``, ``logl``, ``weights``, optional ``ref``) to skip
     the host staging (used by ``bench.py`` for the inputs-resident measurement).
@@ -98,10 +101,38 @@ def evidence_sharded(samples, logl, weights, kmax, ref=None, ndim=None, priorvol
             dist.broadcast(t, src=0, group=group)
             return t
 
-        tens = {'samples': bcast(samples[:, :nd] if rank == 0 else None, (n, nd)),
-                'logl': bcast(logl, (n,)), 'weights': bcast(weights, (n,))}
-        if n_ref:
-            tens['ref'] = bcast(ref[:, :nd] if rank == 0 else None, (n_ref, nd))
+        def gather_rows(arr, cols):
+            """Every rank holds ``arr``: upload rows [rank*c, (rank+1)*c) and all-gather the blocks."""
+            c = -(-n_rows[0] // world)
+            lo, hi = min(rank * c, n_rows[0]), min((rank + 1) * c, n_rows[0])
+            shape = (world * c, cols) if cols else (world * c,)
+            full = torch.empty(shape, dtype=torch.float64, device=device if use_cuda else 'cpu')
+            mine = full[rank * c:(rank + 1) * c]
+            if hi > lo:
+                src = torch.from_numpy(np.ascontiguousarray(arr[lo:hi], dtype=np.float64))
+                mine[:hi - lo].copy_(src, non_blocking=True)
+            if hi - lo < c:
+                mine[hi - lo:].zero_()
+            if use_cuda:
+                dist.all_gather_into_tensor(full, mine, group=group)
+            else:
+                parts = [torch.empty_like(mine) for _ in range(world)]
+                dist.all_gather(parts, mine.clone(), group=group)
+                full = torch.cat(parts)
+            return full[:n_rows[0]]
+
+        n_rows = [n]
+        if host_on_every_rank and world > 1:
+            samples = np.asarray(samples)
+            tens = {'samples': gather_rows(samples[:, :nd], nd), 'logl': gather_rows(logl, 0), 'weights': gather_rows(weights, 0)}
+            if n_ref:
+                n_rows[0] = n_ref
+                tens['ref'] = gather_rows(np.asarray(ref)[:, :nd], nd)
+        else:
+            tens = {'samples': bcast(samples[:, :nd] if rank == 0 else None, (n, nd)),
+                    'logl': bcast(logl, (n,)), 'weights': bcast(weights, (n,))}
+            if n_ref:
+                tens['ref'] = bcast(ref[:, :nd] if rank == 0 else None, (n_ref, nd))
     else:
         tens = resident
         n, nd = tens['samples'].shape

@@ -54,7 +54,7 @@ def _oracle_compute(arrays, q_range):
     return np.array(parts), math.log(cs['J']), {}
 
 
-def _worker(rank, world, port, cross, q):
+def _worker(rank, world, port, cross, q, replicated=False):
     import torch.distributed as dist
     from mcevidence_b200.dist import evidence_sharded
     from mcevidence_b200.synthetic import gaussian_chain
@@ -64,15 +64,15 @@ def _worker(rank, world, port, cross, q):
     try:
         args = (None, None, None, 4)
         kw = {}
-        if rank == 0:
-            c, _ = gaussian_chain(900, 5, seed=7)
+        if rank == 0 or replicated:
+            c, _ = gaussian_chain(901 if replicated else 900, 5, seed=7)
             if cross:
                 args = (c[:400, 2:], -c[:400, 1], c[:400, 0], 4)
                 kw = {'ref': c[400:, 2:]}
             else:
                 args = (c[:, 2:], -c[:, 1], c[:, 0], 4)
             kw['priorvolume'] = 2.0
-        out = evidence_sharded(*args, compute=_oracle_compute, **kw)
+        out = evidence_sharded(*args, compute=_oracle_compute, host_on_every_rank=replicated, **kw)
         q.put((rank, out['logE'], out['q_range']))
     finally:
         dist.destroy_process_group()
@@ -104,4 +104,34 @@ def test_sharded_evidence_two_ranks_gloo(cross):
         want = O.evidence(c[:, 2:], -c[:, 1], c[:, 0], 5, 4, priorvolume=2.0, knn='brute')
         assert res[0][2] == (0, 450) and res[1][2] == (450, 900)
     np.testing.assert_array_equal(res[0][1], res[1][1])          # every rank ends with the same answer
+    assert np.abs(res[0][1] - want).max() < 1e-10
+
+
+@pytest.mark.parametrize('cross', [False, True])
+def test_sharded_evidence_host_arrays_on_every_rank(cross):
+    """Every rank holds the chain (as the ranks of the reference's MPI driver do): each uploads its own block of rows, the
+    blocks are all-gathered (odd row count: the last block is padded) and the answer equals the single-process one."""
+    import torch.multiprocessing as mp
+    from oracle import mce_oracle as O
+    from mcevidence_b200.synthetic import gaussian_chain
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, cross, q, True)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    c, _ = gaussian_chain(901, 5, seed=7)
+    if cross:
+        want = O.evidence(c[:400, 2:], -c[:400, 1], c[:400, 0], 5, 4, s2=c[400:, 2:], priorvolume=2.0, knn='brute')
+    else:
+        want = O.evidence(c[:, 2:], -c[:, 1], c[:, 0], 5, 4, priorvolume=2.0, knn='brute')
+        assert res[0][2] == (0, 451) and res[1][2] == (451, 901)
+    np.testing.assert_array_equal(res[0][1], res[1][1])
     assert np.abs(res[0][1] - want).max() < 1e-10

@@ -41,6 +41,17 @@ for cross in (False, True):
     gathered = [None] * world
     dist.all_gather_object(gathered, [float(x) for x in out['logE']])
     ok &= all(g == gathered[0] for g in gathered)
+    # the same with the chain on every rank's host: each rank uploads its own block of rows, the blocks are all-gathered
+    c, _ = gaussian_chain(200003, 8, seed=3, nextra=1)
+    if cross:
+        args2, kw2 = (c[:90001, 2:], -c[:90001, 1], c[:90001, 0], 4), {'ref': c[90001:, 2:], 'ndim': 8}
+    else:
+        args2, kw2 = (c[:, 2:], -c[:, 1], c[:, 0], 4), {'ndim': 8}
+    out2 = evidence_sharded(*args2, priorvolume=3.0, host_on_every_rank=True, **kw2)
+    same = bool(np.array_equal(out2['logE'], out['logE']))
+    if rank == 0:
+        print('cross=%d host arrays on every rank: identical to the broadcast path: %s' % (cross, same), flush=True)
+    ok &= same
 # chain-per-GPU batching: every rank passes the same list, results gathered
 chains = [gaussian_chain(n, d, seed=40 + i, integer_weights=True, inflate=1.0)[0]
           for i, (n, d) in enumerate([(3000, 6), (9000, 7), (5000, 8), (2000, 9), (7000, 7), (4000, 6)])]
