@@ -52,13 +52,7 @@
 #define TC_BOOT_TILES 128   // tiles of a (long) unit that are first looked at for the threshold only (even; 0 = first tile only)
 #endif
 #ifndef TC_BOOT_DIV
-#define TC_BOOT_DIV 12
-#endif
-#ifndef TC_SPLIT_LD
-#define TC_SPLIT_LD 0       // 1: the 64 columns are loaded as two 32-column halves, the max of the first taken while the second arrives
-#endif
-#ifndef TC_FENCE_ACQREL
-#define TC_FENCE_ACQREL 0   // 1: fence.acq_rel.cta instead of __threadfence_block() (MEMBAR.SC.CTA) on the slab path
+#define TC_BOOT_DIV 12      // ... over nt / 12 tiles at most (nt / 6 for units shorter than 128 tiles)
 #endif
 #ifndef TC_SEL_MIN
 #define TC_SEL_MIN 32       // the selection warp evaluates a batch when at least this many hits are waiting
@@ -413,11 +407,7 @@ __device__ __forceinline__ void tc_process_tile(const uint32_t (&v)[TC_HALF_COLS
                     for (int j = 0; j < 8; ++j)
                         sts_b32x4(slab + 16u * j, v[32 * g + 4 * j], v[32 * g + 4 * j + 1], v[32 * g + 4 * j + 2], v[32 * g + 4 * j + 3]);
                     sts_u32_volatile(hdr, 0x80000000u | (uint32_t)(ridx0 + col_base + 32 * g));
-#if TC_FENCE_ACQREL
-                    asm volatile("fence.acq_rel.cta;" ::: "memory");
-#else
                     __threadfence_block();
-#endif
                     reds_or_u32(pend, 1u << (threadIdx.x & 31));
                 }
             }
@@ -987,20 +977,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_filter_tc_kernel(const TcFi
             if constexpr (MODE <= 2 || MODE == 5) {
                 const float tcut = lds_f32_volatile(st.th_addr) - e_q;
                 uint32_t v[TC_HALF_COLS];
-#if TC_SPLIT_LD
-                {
-                    uint32_t(&va)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
-                    uint32_t(&vb)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
-                    tmem_ld32(taddr, va);
-                    tmem_wait_ld(va);
-                    tmem_ld32(taddr + 32u, vb);
-                    const float m0 = max32(&v[0]);
-                    asm volatile("" ::"f"(m0));   // taken while the second half is in flight
-                    tmem_wait_ld(vb);
-                }
-#else
                 tmem_ld64_wait(taddr, v);
-#endif
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
