@@ -16,3 +16,14 @@ def test_allowance_covers_tf32_truncation(d, L):
     assert r['max_ratio'] < 0.8                       # worst emulated |coarse - exact| / e
     assert r['inserts'] == r['ffma_inserts']          # no reference an exact-threshold filter keeps is dropped
     assert r['visits'] < 1.6 * r['inserts'] + 2       # the allowance adds few slow-path visits at these ndim
+
+
+@pytest.mark.parametrize('d,L,boot', [(6, 4, 16), (10, 5, 32), (20, 11, 32)])
+def test_multi_tile_bootstrap_threshold_is_valid(d, L, boot):
+    """The start threshold of the multi-tile bootstrap (group maxima of the first `boot` tiles per column half, the
+    (L+1)-th largest minus the allowance) never exceeds what L references other than the query itself reach exactly, the
+    scan that starts from it ends with the exact top-L list, and it sends fewer columns to the slow path than a scan
+    that starts from the first tile alone."""
+    r = tc_model.bootstrap_model(30000, d, 40, L, boot, seed=5)
+    assert r['valid'] and r['lists_exact']
+    assert r['visits_boot'] < r['visits_first_tile']
